@@ -1,0 +1,113 @@
+/*
+ * bp_b200.h -- C ABI of the B200-native batched belief-propagation decoder.
+ *
+ * This is the drop-in boundary for the BP / BP+OSD syndrome-decoding path of
+ * quantumgizmos/ldpc (reference paths relative to /root/reference).  Today that
+ * boundary is the Cython extern block src_python/ldpc/bp_decoder/_bp_decoder.pxd:9-83
+ * (class ldpc::bp::BpDecoder, src_cpp/bp.hpp:51-132, driven by direct member access) and
+ * src_python/ldpc/bposd_decoder/_bposd_decoder.pxd:9-29 (ldpc::osd::OsdDecoder,
+ * src_cpp/osd.hpp:26-189).  A maintainer re-points those extern blocks at the functions
+ * below (INTEGRATION.md shows the stub).  Plain C: opaque handle, raw pointers + sizes, no
+ * exceptions, no torch / C++ types.  Every function returns BPB_OK (0) or a negative code;
+ * bpb_last_error() gives the message.
+ *
+ * Enumerations use the reference's numeric values (bp.hpp:23-38, osd.hpp:18-23).
+ *
+ * Ownership: the caller owns every host/device array it passes; the library copies the
+ * parity-check matrix and the channel at create/set time and owns all device workspaces.
+ * Threading: one handle = one logical decoder bound to one CUDA device; calls on one handle
+ * must not overlap; distinct handles are independent.
+ */
+#ifndef BP_B200_H
+#define BP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bpb_decoder bpb_decoder;
+
+enum { BPB_OK = 0, BPB_ERR_ARG = -1, BPB_ERR_CUDA = -2, BPB_ERR_UNSUPPORTED = -3, BPB_ERR_NOMEM = -4 };
+
+/* ldpc::bp::BpMethod, bp.hpp:23-26 */
+enum { BPB_PRODUCT_SUM = 0, BPB_MINIMUM_SUM = 1 };
+/* ldpc::bp::BpSchedule, bp.hpp:28-32 (SERIAL_RELATIVE = 2 is not offered on the GPU) */
+enum { BPB_SERIAL = 0, BPB_PARALLEL = 1 };
+/* ldpc::bp::BpInputType, bp.hpp:34-38 */
+enum { BPB_INPUT_SYNDROME = 0, BPB_INPUT_RECEIVED_VECTOR = 1 };
+/* kernel family: AUTO picks the fastest family that supports the code */
+enum { BPB_KERNEL_AUTO = 0, BPB_KERNEL_STREAM = 1, BPB_KERNEL_SMEM = 2 };
+
+/* --- life cycle ------------------------------------------------------------------------------
+ * Replaces `new BpSparse(m,n,nnz)` + insert_entry per nonzero (_bp_decoder.pyx:9-49) and
+ * `new BpDecoderCpp(...)` (_bp_decoder.pyx:132, bp.hpp:77-132).  (rows[k], cols[k]) are the
+ * nonzeros of H in any order; they are sorted into the reference's traversal order
+ * (sparse_matrix_base.hpp:423-482).  `device` is the CUDA ordinal (device < 0 creates a host-only handle on
+ * which only bpb_osd0_host works; decode calls on it fail -- there is no CPU decode path).  Defaults after create are the
+ * reference constructor's: product_sum, parallel, ms_scaling_factor 0.625... overwritten by the
+ * shim exactly as the Cython shim does (_bp_decoder.pyx:135-155). */
+int bpb_create(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *cols, int device, bpb_decoder **out);
+void bpb_destroy(bpb_decoder *h);
+const char *bpb_last_error(const bpb_decoder *h); /* h may be NULL: last create error */
+
+/* --- parameters: replace writes to public members of BpDecoder (bp.hpp:55-74) --------------- */
+int bpb_set_channel(bpb_decoder *h, const double *channel_probabilities, int n); /* bp.hpp:55 */
+int bpb_set_max_iter(bpb_decoder *h, int maximum_iterations);                    /* bp.hpp:58 */
+int bpb_set_method(bpb_decoder *h, int bp_method);                               /* bp.hpp:59 */
+int bpb_set_schedule(bpb_decoder *h, int schedule);                              /* bp.hpp:60 */
+int bpb_set_ms_scaling_factor(bpb_decoder *h, double ms_scaling_factor);         /* bp.hpp:62 */
+int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len); /* bp.hpp:69; NULL = 0..n-1 */
+int bpb_set_kernel(bpb_decoder *h, int kernel_family);                           /* new: BPB_KERNEL_* */
+
+/* --- decode: replaces BpDecoder::decode(vector<uint8_t>&) (bp.hpp:159-190) for a whole batch --
+ * input  : [batch][m] (syndromes) or [batch][n] (received vectors), uint8 0/1, row-major
+ * outputs: decoding [batch][n] uint8 (bp.hpp:63), converged [batch] uint8 (bp.hpp:72),
+ *          iterations [batch] int32 (bp.hpp:70), log_prob_ratios [batch][n] double (bp.hpp:66).
+ *          converged / iterations / log_prob_ratios may be NULL.
+ * Every syndrome is decoded exactly as one BpDecoder::decode call would (including the per-syndrome
+ * early exit, bp.hpp:300-308, 539-542); results do not depend on batch order or size.
+ *
+ * bpb_decode_batch takes HOST pointers (pageable or pinned) and includes the H2D/D2H copies.
+ * bpb_decode_batch_device takes DEVICE pointers on the handle's device and enqueues everything on
+ * `cuda_stream` (a cudaStream_t passed as void*, NULL = default stream) without synchronising. */
+int bpb_decode_batch(bpb_decoder *h, int input_type, const uint8_t *input, int64_t batch, uint8_t *decoding,
+                     uint8_t *converged, int32_t *iterations, double *log_prob_ratios);
+int bpb_decode_batch_device(bpb_decoder *h, int input_type, const uint8_t *d_input, int64_t batch,
+                            uint8_t *d_decoding, uint8_t *d_converged, int32_t *d_iterations,
+                            double *d_log_prob_ratios, void *cuda_stream);
+
+/* --- OSD-0 post-processing on the host (replaces OsdDecoder::decode with osd_order 0,
+ * osd.hpp:110-117 -> sort.hpp:48-62 + gf2sparse_linalg.hpp:298-401).  For every b with
+ * converged[b] == 0 the row decoding[b] is overwritten with the OSD-0 solution computed from
+ * syndromes[b] and log_prob_ratios[b]; rows with converged[b] != 0 are left alone
+ * (_bposd_decoder.pyx:128-134).  `threads` <= 0 means all hardware threads. */
+int bpb_osd0_host(bpb_decoder *h, const uint8_t *syndromes, const double *log_prob_ratios,
+                  const uint8_t *converged, int64_t batch, uint8_t *decoding, int threads);
+
+/* --- introspection ----------------------------------------------------------------------------- */
+typedef struct {
+    int m, n;
+    int64_t nnz;
+    int max_row_degree, max_col_degree;
+    int device, sm_count;
+    int kernel_family;        /* family used by the last decode */
+    int grid, block;          /* launch shape of the last message-update kernel */
+    int64_t launches;         /* kernels launched by this handle so far */
+    int64_t workspace_bytes;  /* device bytes held */
+    double last_kernel_ms;    /* CUDA-event time of the last message-update kernel, 0 until it has finished */
+} bpb_info;
+int bpb_get_info(const bpb_decoder *h, bpb_info *out);
+
+/* Pinned host memory helpers for callers that want full-speed H2D/D2H (optional). */
+void *bpb_host_alloc(size_t bytes);
+void bpb_host_free(void *p);
+
+const char *bpb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BP_B200_H */

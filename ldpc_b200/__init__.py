@@ -1,0 +1,12 @@
+"""ldpc_b200 -- B200-native batched belief-propagation decoding behind the quantumgizmos/ldpc API.
+
+``BpDecoder`` / ``BpOsdDecoder`` keep the reference package's constructor arguments and ``.decode(syndrome)``
+(reference src_python/ldpc/bp_decoder, src_python/ldpc/bposd_decoder) and add ``.decode_batch``.  The work is
+done by hand-written sm_100a CUDA kernels in ``ldpc_b200/csrc`` behind the C-ABI of ``include/bp_b200.h``.
+"""
+from .bp_decoder import BpDecoder, BpDecoderBase, io_test
+from .bposd_decoder import BpOsdDecoder
+from . import codes
+
+__all__ = ["BpDecoder", "BpDecoderBase", "BpOsdDecoder", "io_test", "codes"]
+__version__ = "0.1.0"

@@ -1,0 +1,65 @@
+// bp_decoder.h -- internal state behind the opaque bpb_decoder handle (include/bp_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bp_b200.h"
+
+namespace bpb {
+
+// Host copy of H in the reference's traversal order (sparse_matrix_base.hpp:423-482):
+// CSR with ascending columns per row, CSC with ascending rows per column.
+struct HostGraph {
+    int m = 0, n = 0, nnz = 0;
+    std::vector<uint32_t> row_ptr, col_idx;            // CSR
+    std::vector<uint32_t> col_ptr, row_idx, csc2csr;   // CSC; csc2csr: CSC position -> CSR edge id
+    int max_row_degree = 0, max_col_degree = 0;
+};
+
+int build_host_graph(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *cols, HostGraph &g,
+                     std::string &err);
+
+// Bit-packed OSD-0 on the host (osd_host.cpp).
+int osd0_host(const HostGraph &g, const uint8_t *syndromes, const double *llr, const uint8_t *converged,
+              int64_t batch, uint8_t *decoding, int threads);
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace bpb
+
+struct bpb_decoder {
+    bpb::HostGraph g;
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    // parameters (reference BpDecoder members, bp.hpp:55-74)
+    std::vector<double> channel;
+    std::vector<double> prior;  // log((1-p)/p) computed on the host with libm like bp.hpp:150-151
+    bool uniform_prior = true;
+    int max_iter = 0;
+    int method = BPB_PRODUCT_SUM;
+    int schedule = BPB_PARALLEL;
+    double ms_scaling = 0.625;
+    std::vector<uint32_t> serial_order;
+    int kernel_pref = BPB_KERNEL_AUTO;
+    // device state
+    bool graph_dirty = true;  // blob must be (re)uploaded (prior or order changed)
+    bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed;
+    // staging for the host API
+    bpb::DeviceBuffer st_in, st_dec, st_conv, st_iters, st_llr;
+    uint32_t blob_words = 0, prior_off = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr;
+    bool kernel_timed = false;
+    // info
+    int last_family = 0, last_grid = 0, last_block = 0;
+    int64_t launches = 0;
+    double last_kernel_ms = 0.0;
+    std::string err;
+};

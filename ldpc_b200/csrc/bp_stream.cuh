@@ -1,0 +1,395 @@
+// bp_stream.cuh -- the HBM-streaming kernel family ("one lane = one syndrome").
+//
+// Replaces ldpc::bp::BpDecoder::bp_decode_parallel (reference src_cpp/bp.hpp:192-325) and
+// bp_decode_serial (bp.hpp:451-545) for a whole batch of syndromes sharing one read-only H.
+//
+// Layout in HBM.  A warp owns a *tile* of 32 in-flight syndromes.  The tile's messages are one
+// array msg[e][lane] of doubles, e = CSR edge id (rows ascending, columns ascending inside a row,
+// i.e. the reference's iterate_row order, sparse_matrix_base.hpp:423-482), so every message access of a
+// warp is one fully coalesced 256-byte transaction and a whole check row is d_c*256 contiguous bytes.
+// The reference keeps two doubles per edge (bit_to_check_msg, check_to_bit_msg, bp.hpp:42-48); here
+// one slot per edge suffices because each half-iteration reads a row (column) completely before it
+// overwrites it: the check pass turns b2c into c2b in place, the bit pass turns c2b back into b2c.
+//
+// Early exit.  Lanes are persistent: when a lane's syndrome converges (bp.hpp:300-308) or reaches
+// maximum_iterations it writes decoding/iterations/converge(/log_prob_ratios) for that syndrome and
+// claims the next unclaimed syndrome from a global counter.  Lanes of one warp may therefore be at
+// different iteration numbers; the control flow only depends on H, which all lanes share.
+//
+// Hard decisions are exchanged as ballot words: dec_w[j] holds bit `lane` = decoding[j] of that lane's
+// syndrome; syn_w[i] likewise for the syndrome.  The candidate-syndrome test of bp.hpp:292-300 then
+// costs one XOR per (row, column) pair per warp instead of per syndrome.
+#pragma once
+#include "bp_common.cuh"
+#include "bp_stream_params.h"
+
+namespace bpb {
+
+template <int DC> struct RowsPerBatch { static constexpr int v = DC <= 8 ? 2 : 1; };
+template <int DV> struct ColsPerBatch { static constexpr int v = DV <= 4 ? 4 : 1; };
+
+template <int METHOD, int SCHED, int DC, int DV, bool LLR>
+__global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const long long gw = (long long) blockIdx.x * wpb + wib;
+    const int m = p.m, n = p.n, nnz = p.nnz;
+
+    const uint32_t *base = p.blob;
+    if (p.smem_graph) {
+        for (uint32_t i = threadIdx.x; i < p.blob_words; i += blockDim.x) smem[i] = p.blob[i];
+        __syncthreads();
+        base = smem;
+    }
+    const uint32_t *row_ptr = base;
+    const uint32_t *col_idx = row_ptr + (m + 1);
+    const uint32_t *col_ptr = col_idx + nnz;
+    const uint32_t *csc2csr = col_ptr + (n + 1);
+    const uint32_t *row_idx = csc2csr + nnz;
+    const double *prior = reinterpret_cast<const double *>(base + p.prior_off);
+    (void) row_idx;
+
+    uint32_t *syn_w = p.smem_syn ? (smem + p.smem_syn_off + (size_t) wib * p.m_pad) : (p.syn_w_g + gw * p.m_pad);
+    uint32_t *dec_w = p.dec_w + gw * p.n_pad;
+    double *tile = p.msg + (size_t) gw * (size_t) nnz * 32 + lane;
+    double *llr_tile = LLR ? (p.llr_tile + (size_t) gw * (size_t) n * 32 + lane) : nullptr;
+
+    long long idx = -1;  // syndrome this lane is decoding, -1 = idle
+    int it = 0;
+    bool exhausted = false;  // warp-uniform: the global queue is empty
+
+    for (;;) {
+        // ---------------- claim work -----------------------------------------------------------------
+        const bool need = (idx < 0) && !exhausted;
+        const uint32_t needmask = __ballot_sync(0xffffffffu, need);
+        if (needmask) {
+            unsigned long long first_idx = 0;
+            if (lane == 0) first_idx = atomicAdd(p.counter, (unsigned long long) __popc(needmask));
+            first_idx = __shfl_sync(0xffffffffu, first_idx, 0);
+            bool fresh = false;
+            if (need) {
+                const long long mine = (long long) first_idx + __popc(needmask & lanemask_lt());
+                if (mine < p.batch) {
+                    idx = mine;
+                    it = 0;
+                    fresh = true;
+                }
+            }
+            if ((long long) first_idx + __popc(needmask) >= p.batch) exhausted = true;
+            const uint32_t newmask = __ballot_sync(0xffffffffu, fresh);
+            if (newmask) {
+                // transpose the new lanes' packed syndromes into ballot words
+                const uint32_t *srow = p.synd_packed + (fresh ? idx : 0) * p.mwp;
+                for (int w = 0; w * 32 < m; ++w) {
+                    const uint32_t v = fresh ? __ldg(srow + w) : 0u;
+                    uint32_t mine_w = 0;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const uint32_t t = __ballot_sync(0xffffffffu, (v >> r) & 1u);
+                        if (lane == r) mine_w = t;
+                    }
+                    const int i = w * 32 + lane;
+                    if (i < m) syn_w[i] = (syn_w[i] & ~newmask) | (mine_w & newmask);
+                }
+                if (SCHED == kSerial) {
+                    // explicit initialise_log_domain_bp (bp.hpp:147-157) for the new lanes
+                    if (fresh)
+                        for (int e = 0; e < nnz; ++e)
+                            st_msg(tile + (size_t) e * 32, p.uniform_prior ? p.prior0 : prior[col_idx[e]]);
+                }
+                __syncwarp();
+            }
+        }
+        const bool active = idx >= 0;
+        const uint32_t actmask = __ballot_sync(0xffffffffu, active);
+        if (!actmask) break;
+        it += 1;
+        const bool first = (it == 1);
+        const bool any_first = __any_sync(0xffffffffu, active && first);
+        const double alpha = ms_alpha(p.ms_scaling, it);
+        (void) alpha;
+        (void) any_first;
+
+        if (SCHED == kParallel) {
+            // ---------------- check -> bit (bp.hpp:201-273), in place --------------------------------
+            constexpr int RB = RowsPerBatch<DC>::v;
+            for (int i0 = 0; i0 < m; i0 += RB) {
+                uint32_t beg[RB];
+                int deg[RB];
+                double b[RB][DC];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const int i = i0 + r;
+                    if (i < m) {
+                        beg[r] = row_ptr[i];
+                        deg[r] = (int) (row_ptr[i + 1] - beg[r]);
+                    } else {
+                        beg[r] = 0;
+                        deg[r] = 0;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) {
+                        double v = p.prior0;
+                        if (k < deg[r]) {
+                            if (any_first && !p.uniform_prior) v = prior[col_idx[beg[r] + k]];
+                            if (active && !first) v = ld_msg(tile + (size_t) (beg[r] + k) * 32);
+                        }
+                        b[r][k] = v;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const int i = i0 + r;
+                    if (i >= m) continue;
+                    const uint32_t s = (syn_w[i] >> lane) & 1u;
+                    double c[DC];
+                    if (METHOD == kMinimumSum) {
+                        // bp.hpp:231-271: total sign, min over the other edges, scaled
+                        uint32_t tsgn = s;
+                        double min1 = DBL_MAX, min2 = DBL_MAX;
+                        int arg = -1;
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) {
+                            if (k < deg[r]) {
+                                if (b[r][k] <= 0) tsgn += 1;
+                                const double a = fabs(b[r][k]);
+                                if (a < min1) {
+                                    min2 = min1;
+                                    min1 = a;
+                                    arg = k;
+                                } else if (a < min2) {
+                                    min2 = a;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) {
+                            if (k < deg[r]) {
+                                const double mag = (k == arg) ? min2 : min1;
+                                const uint32_t sg = tsgn + ((b[r][k] <= 0) ? 1u : 0u);
+                                c[k] = mag * ((sg & 1u) ? -alpha : alpha);
+                            }
+                        }
+                    } else {
+                        // bp.hpp:202-218: prefix products forward, suffix products backward
+                        double t[DC];
+                        double pre = 1.0;
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) {
+                            if (k < deg[r]) {
+                                t[k] = ref_tanh(b[r][k] / 2);
+                                c[k] = pre;
+                                pre *= t[k];
+                            }
+                        }
+                        double suf = 1.0;
+                        const double sigma = s ? -1.0 : 1.0;
+#pragma unroll
+                        for (int k = DC - 1; k >= 0; --k) {
+                            if (k < deg[r]) {
+                                const double x = c[k] * suf;
+                                c[k] = sigma * log((1 + x) / (1 - x));
+                                suf *= t[k];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < DC; ++k)
+                        if (active && k < deg[r]) st_msg(tile + (size_t) (beg[r] + k) * 32, c[k]);
+                }
+            }
+            // ---------------- bit pass: posterior, decision, b2c (bp.hpp:276-318), in place ----------
+            constexpr int CB = ColsPerBatch<DV>::v;
+            uint32_t acc_w = 0;
+            for (int j0 = 0; j0 < n; j0 += CB) {
+                uint32_t eid[CB][DV];
+                int deg[CB];
+                double c[CB][DV];
+#pragma unroll
+                for (int r = 0; r < CB; ++r) {
+                    const int j = j0 + r;
+                    uint32_t beg = 0;
+                    deg[r] = 0;
+                    if (j < n) {
+                        beg = col_ptr[j];
+                        deg[r] = (int) (col_ptr[j + 1] - beg);
+                    }
+#pragma unroll
+                    for (int k = 0; k < DV; ++k) eid[r][k] = (k < deg[r]) ? csc2csr[beg + k] : 0u;
+                }
+#pragma unroll
+                for (int r = 0; r < CB; ++r) {
+#pragma unroll
+                    for (int k = 0; k < DV; ++k) {
+                        double v = 0.0;
+                        if (active && k < deg[r]) v = ld_msg(tile + (size_t) eid[r][k] * 32);
+                        c[r][k] = v;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < CB; ++r) {
+                    const int j = j0 + r;
+                    if (j >= n) continue;
+                    double pre[DV];
+                    double t = p.uniform_prior ? p.prior0 : prior[j];
+#pragma unroll
+                    for (int k = 0; k < DV; ++k) {
+                        if (k < deg[r]) {
+                            pre[k] = t;
+                            t += c[r][k];
+                        }
+                    }
+                    const bool x = (t <= 0);
+                    if (LLR) {
+                        if (active) llr_tile[(size_t) j * 32] = t;
+                    }
+                    const uint32_t W = __ballot_sync(0xffffffffu, active && x);
+                    if (lane == (j & 31)) acc_w = W;
+                    if ((j & 31) == 31 || j == n - 1) dec_w[(j & ~31) + lane] = acc_w;
+                    double u = 0;
+#pragma unroll
+                    for (int k = DV - 1; k >= 0; --k) {
+                        if (k < deg[r]) {
+                            const double bn = pre[k] + u;
+                            u += c[r][k];
+                            if (active) st_msg(tile + (size_t) eid[r][k] * 32, bn);
+                        }
+                    }
+                }
+            }
+        } else {
+            // ---------------- serial schedule (bp.hpp:484-534) ----------------------------------------
+            for (int oi = 0; oi < p.order_len; ++oi) {  // one bit at a time, in schedule order
+                const int j = (int) p.order[oi];
+                const uint32_t cbeg = col_ptr[j];
+                const int cdeg = (int) (col_ptr[j + 1] - cbeg);
+                double L = p.uniform_prior ? p.prior0 : prior[j];
+                double c[DV], pre[DV];
+                uint32_t eid[DV];
+#pragma unroll
+                for (int k = 0; k < DV; ++k) {
+                    if (k < cdeg) {
+                        const uint32_t e = csc2csr[cbeg + k];
+                        const uint32_t i = row_idx[cbeg + k];
+                        const uint32_t rbeg = row_ptr[i];
+                        const int rdeg = (int) (row_ptr[i + 1] - rbeg);
+                        const uint32_t s = (syn_w[i] >> lane) & 1u;
+                        eid[k] = e;
+                        double bv[DC];
+#pragma unroll
+                        for (int f = 0; f < DC; ++f) {
+                            double v = 0.0;
+                            if (active && f < rdeg && rbeg + f != e) v = ld_msg(tile + (size_t) (rbeg + f) * 32);
+                            bv[f] = v;
+                        }
+                        if (METHOD == kMinimumSum) {
+                            uint32_t sg = s;
+                            double temp = DBL_MAX;
+#pragma unroll
+                            for (int f = 0; f < DC; ++f) {
+                                if (f < rdeg && rbeg + f != e) {
+                                    const double a = fabs(bv[f]);
+                                    if (a < temp) temp = a;
+                                    if (bv[f] <= 0) sg += 1;
+                                }
+                            }
+                            c[k] = ((sg & 1u) ? -alpha : alpha) * temp;
+                        } else {
+                            double x = 1.0;
+#pragma unroll
+                            for (int f = 0; f < DC; ++f)
+                                if (f < rdeg && rbeg + f != e) x *= ref_tanh(bv[f] / 2);
+                            c[k] = (s ? -1.0 : 1.0) * log((1 + x) / (1 - x));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < DV; ++k) {
+                    if (k < cdeg) {
+                        pre[k] = L;
+                        L += c[k];
+                    }
+                }
+                const bool x = (L <= 0);
+                if (LLR) {
+                    if (active) llr_tile[(size_t) j * 32] = L;
+                }
+                const uint32_t W = __ballot_sync(0xffffffffu, active && x);
+                if (lane == 0) dec_w[j] = W;
+                double u = 0;
+#pragma unroll
+                for (int k = DV - 1; k >= 0; --k) {
+                    if (k < cdeg) {
+                        const double bn = pre[k] + u;
+                        u += c[k];
+                        if (active) st_msg(tile + (size_t) eid[k] * 32, bn);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---------------- candidate syndrome == syndrome ?  (bp.hpp:292-308 / 537-542) ---------------
+        uint32_t mis = 0;
+        for (int i = lane; i < m; i += 32) {
+            uint32_t cs = 0;
+            const uint32_t rb = row_ptr[i], re = row_ptr[i + 1];
+            for (uint32_t e = rb; e < re; ++e) cs ^= __ldcg(dec_w + col_idx[e]);
+            mis |= cs ^ syn_w[i];
+        }
+        mis = __reduce_or_sync(0xffffffffu, mis);
+        const bool conv = active && !((mis >> lane) & 1u);
+        const bool done = active && (conv || it >= p.max_iter);
+        uint32_t donemask = __ballot_sync(0xffffffffu, done);
+
+        // ---------------- retire finished syndromes ------------------------------------------------
+        while (donemask) {
+            const int l = __ffs(donemask) - 1;
+            donemask &= donemask - 1;
+            const long long oidx = __shfl_sync(0xffffffffu, idx, l);
+            const int oit = __shfl_sync(0xffffffffu, it, l);
+            const int oconv = __shfl_sync(0xffffffffu, (int) conv, l);
+            uint8_t *drow = p.out_dec + oidx * n;
+            if ((n & 3) == 0) {
+                for (int j = lane * 4; j < n; j += 128) {
+                    const uint4 w4 = __ldcg(reinterpret_cast<const uint4 *>(dec_w + j));
+                    const uint32_t packed = ((w4.x >> l) & 1u) | (((w4.y >> l) & 1u) << 8) |
+                                            (((w4.z >> l) & 1u) << 16) | (((w4.w >> l) & 1u) << 24);
+                    *reinterpret_cast<uint32_t *>(drow + j) = packed;
+                }
+            } else {
+                for (int j = lane; j < n; j += 32) drow[j] = (uint8_t) ((__ldcg(dec_w + j) >> l) & 1u);
+            }
+            if (lane == 0) {
+                if (p.out_iters) p.out_iters[oidx] = oit;
+                if (p.out_conv) p.out_conv[oidx] = (uint8_t) oconv;
+            }
+            if (LLR) {
+                const double *src = p.llr_tile + (size_t) gw * (size_t) n * 32 + l;
+                double *dst = p.out_llr + oidx * n;
+                for (int j = lane; j < n; j += 32) dst[j] = __ldcg(src + (size_t) j * 32);
+            }
+        }
+        if (done) idx = -1;
+    }
+}
+
+// One translation unit per (method, schedule) instantiates its degree buckets through this helper.
+template <int METHOD, int SCHED>
+StreamKernel pick_stream_bucket(int dc, int dv, bool llr) {
+#define BPB_PICK(DC_, DV_) \
+    return llr ? bp_stream_kernel<METHOD, SCHED, DC_, DV_, true> : bp_stream_kernel<METHOD, SCHED, DC_, DV_, false>
+    if (dc <= 8 && dv <= 4) { BPB_PICK(8, 4); }
+    if (dc <= 8 && dv <= 16) { BPB_PICK(8, 16); }
+    if (dc <= 32 && dv <= 4) { BPB_PICK(32, 4); }
+    if (dc <= 32 && dv <= 16) { BPB_PICK(32, 16); }
+#undef BPB_PICK
+    return nullptr;
+}
+
+}  // namespace bpb

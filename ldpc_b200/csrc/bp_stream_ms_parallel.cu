@@ -1,0 +1,5 @@
+// Instantiates the ms / parallel stream kernels (bp_stream.cuh) for every degree bucket.
+#include "bp_stream.cuh"
+namespace bpb {
+StreamKernel pick_stream_ms_parallel(int dc, int dv, bool llr) { return pick_stream_bucket<kMinimumSum, kParallel>(dc, dv, llr); }
+}  // namespace bpb

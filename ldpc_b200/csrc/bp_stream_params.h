@@ -1,0 +1,44 @@
+// bp_stream_params.h -- launch parameters of the HBM-streaming kernel family (see bp_stream.cuh).
+#pragma once
+#include <stdint.h>
+
+namespace bpb {
+
+struct StreamParams {
+    // graph blob: [row_ptr m+1][col_idx nnz][col_ptr n+1][csc2csr nnz][row_idx nnz][pad][prior n doubles]
+    const uint32_t *blob;
+    uint32_t blob_words;  // 32-bit words in the blob
+    uint32_t prior_off;   // word offset of prior[] (even)
+    int m, n, nnz;
+    int mwp;              // 32-bit words per packed syndrome row (multiple of 4)
+    int m_pad, n_pad;     // multiples of 32
+    int max_iter;
+    double ms_scaling;
+    int uniform_prior;
+    double prior0;
+    const uint32_t *synd_packed;  // [B][mwp]
+    long long batch;
+    unsigned long long *counter;
+    double *msg;          // [warps][nnz][32]
+    uint32_t *dec_w;      // [warps][n_pad]
+    uint32_t *syn_w_g;    // [warps][m_pad] (used when the syndrome words do not fit in shared memory)
+    double *llr_tile;     // [warps][n][32] (only when LLRs are requested)
+    uint8_t *out_dec;     // [B][n]
+    uint8_t *out_conv;    // [B] or null
+    int32_t *out_iters;   // [B] or null
+    double *out_llr;      // [B][n] or null
+    const uint32_t *order;  // serial schedule order (device), order_len entries
+    int order_len;
+    int smem_graph, smem_syn;
+    uint32_t smem_syn_off;  // word offset of the per-warp syndrome words in dynamic shared memory
+};
+
+using StreamKernel = void (*)(const StreamParams);
+
+// defined in bp_stream_{ms,ps}_{parallel,serial}.cu; nullptr when no degree bucket fits
+StreamKernel pick_stream_ms_parallel(int max_row_degree, int max_col_degree, bool llr);
+StreamKernel pick_stream_ps_parallel(int max_row_degree, int max_col_degree, bool llr);
+StreamKernel pick_stream_ms_serial(int max_row_degree, int max_col_degree, bool llr);
+StreamKernel pick_stream_ps_serial(int max_row_degree, int max_col_degree, bool llr);
+
+}  // namespace bpb

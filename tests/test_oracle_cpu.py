@@ -1,0 +1,116 @@
+"""CPU: pin the oracle.  (1) the reference's known-answer tests, (2) bit-for-bit agreement of the plain-C
+restatement with the unmodified reference C++ (oracle/_ref) on the BASELINE codes, (3) the committed golden
+fixtures generated from the reference (tests/golden/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from ldpc_b200 import codes
+from kat import KATS, kat_arrays
+from util import assert_same_decode
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _run(oracle_obj, H, kw, inputs, kind):
+    kw = dict(kw)
+    channel = kw.pop("channel")
+    if kind == "received_vector":
+        syn = codes.syndromes_of(H, inputs)
+        out = oracle_obj.decode_batch(H, syn, channel, **kw)
+        return out[0] ^ inputs
+    return oracle_obj.decode_batch(H, inputs, channel, **kw)[0]
+
+
+@pytest.mark.parametrize("entry", KATS, ids=[k[0] for k in KATS])
+def test_port_matches_reference_kats(port_oracle, entry):
+    name, H, kw, inputs, expected, kind = kat_arrays(entry)
+    assert np.array_equal(_run(port_oracle, H, kw, inputs, kind), expected)
+
+
+@pytest.mark.parametrize("entry", KATS, ids=[k[0] for k in KATS])
+def test_ref_matches_its_own_kats(ref_oracle, entry):
+    name, H, kw, inputs, expected, kind = kat_arrays(entry)
+    assert np.array_equal(_run(ref_oracle, H, kw, inputs, kind), expected)
+
+
+CASES = [
+    ("ldpc1000_ms_par", lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 200,
+     dict(max_iter=50, bp_method="ms", schedule="parallel", ms_scaling_factor=0.625)),
+    ("ldpc1000_ms_par_adaptive_hard", lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.09, 60,
+     dict(max_iter=50, bp_method="ms", schedule="parallel", ms_scaling_factor=0.0)),
+    ("ldpc1000_ps_par", lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 80,
+     dict(max_iter=50, bp_method="ps", schedule="parallel")),
+    ("ldpc1000_ps_par_hard", lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.09, 40,
+     dict(max_iter=50, bp_method="ps", schedule="parallel")),
+    ("ldpc1000_ms_ser", lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 100,
+     dict(max_iter=50, bp_method="ms", schedule="serial", ms_scaling_factor=0.625)),
+    ("ldpc1000_ps_ser", lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 40,
+     dict(max_iter=50, bp_method="ps", schedule="serial")),
+    ("surface13_ps", lambda: codes.rotated_surface_code_x(13), 0.05, 400,
+     dict(max_iter=30, bp_method="ps", schedule="parallel")),
+    ("bb144_ms", lambda: codes.bivariate_bicycle_144(), 0.02, 600,
+     dict(max_iter=50, bp_method="ms", schedule="parallel", ms_scaling_factor=0.625)),
+    ("hamming5_ps", lambda: codes.hamming_code(5), 0.1, 100, dict(max_iter=2, bp_method="ps", schedule="parallel")),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_port_bit_identical_to_reference(port_oracle, ref_oracle, case):
+    name, mk, p, B, kw = case
+    H = mk()
+    syn = codes.bsc_syndromes(H, p, B, seed=7)
+    a = port_oracle.decode_batch(H, syn, p, **kw)
+    b = ref_oracle.decode_batch(H, syn, p, **kw)
+    assert_same_decode(a, b, llr_exact=True)
+
+
+def test_port_serial_custom_order_matches_reference(port_oracle, ref_oracle):
+    H = codes.regular_ldpc(200, 3, 6, seed=2)
+    order = np.random.default_rng(4).permutation(200)
+    syn = codes.bsc_syndromes(H, 0.06, 120, seed=9)
+    for method in ("ms", "ps"):
+        kw = dict(max_iter=25, bp_method=method, schedule="serial", ms_scaling_factor=0.9,
+                  serial_schedule_order=order)
+        assert_same_decode(port_oracle.decode_batch(H, syn, 0.06, **kw), ref_oracle.decode_batch(H, syn, 0.06, **kw),
+                           llr_exact=True)
+
+
+def test_port_osd0_matches_reference(port_oracle, ref_oracle):
+    """OSD-0 restatement (oracle/osd_oracle.c) against ldpc::osd::OsdDecoder on BP failures."""
+    for mk, p, B, kw in ((codes.bivariate_bicycle_144, 0.03, 400,
+                          dict(max_iter=20, bp_method="ms", ms_scaling_factor=0.625)),
+                         (lambda: codes.rotated_surface_code_x(7), 0.08, 300, dict(max_iter=10, bp_method="ps")),
+                         (lambda: codes.hamming_code(4), 0.15, 200, dict(max_iter=3, bp_method="ps"))):
+        H = mk()
+        syn = codes.bsc_syndromes(H, p, B, seed=13)
+        dec, conv, its, llr, bpdec = ref_oracle.decode_batch(H, syn, p, osd_method=1, osd_order=0, **kw)
+        bad = ~conv
+        assert bad.any()
+        mine = port_oracle.osd0_batch(H, syn[bad], llr[bad])
+        assert np.array_equal(mine, dec[bad])
+        assert np.array_equal(codes.syndromes_of(H, mine), syn[bad])
+
+
+def test_received_vector_matches_reference(port_oracle, ref_oracle):
+    H = codes.regular_ldpc(120, 3, 6, seed=5)
+    err = codes.bsc_errors(120, 0.05, 100, seed=1)
+    want = ref_oracle.decode_received(H, err, 0.05, 20, bp_method="ps")
+    got = port_oracle.decode_batch(H, codes.syndromes_of(H, err), 0.05, max_iter=20, bp_method="ps")[0] ^ err
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))),
+                         ids=lambda p: os.path.basename(p))
+def test_port_matches_golden_fixture(port_oracle, path):
+    """Fixtures were produced by the unmodified reference (tests/golden/make_golden.py); they travel to
+    machines where /root/reference does not exist."""
+    z = np.load(path, allow_pickle=False)
+    import scipy.sparse as sp
+    H = sp.csr_matrix((np.ones(z["rows"].size, np.uint8), (z["rows"], z["cols"])), shape=tuple(z["shape"]))
+    kw = dict(max_iter=int(z["max_iter"]), bp_method=str(z["bp_method"]), schedule=str(z["schedule"]),
+              ms_scaling_factor=float(z["ms_scaling_factor"]))
+    got = port_oracle.decode_batch(H, z["syndromes"], z["channel"], **kw)
+    assert_same_decode(got, (z["decoding"], z["converged"], z["iters"], z["llr"]), llr_exact=True)
