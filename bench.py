@@ -98,6 +98,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_cores():
+    """CPU threads this process may actually use: min(affinity, cgroup cpu.max quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(round(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def build_code():
     from ldpc_b200 import codes
     return codes.regular_ldpc(N_CODE, DV, DC, seed=CODE_SEED)
@@ -113,7 +125,7 @@ def run_reference(args, rank, world):
     H = build_code()
     if oracle.have_ref():
         impl, kind = oracle.RefOracle(), "reference"
-        cores = os.cpu_count() or 1
+        cores = host_cores()
     else:
         if not oracle.have_port():
             oracle.build()
@@ -303,18 +315,17 @@ def run_ours(args, rank, local_rank, world):
 def cpu_baseline_leg(H, syn_host):
     """Reference C++ (oracle/_ref) or the C port, on a bounded sample of the SAME syndromes (~10-20 s)."""
     import oracle
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     kw = dict(max_iter=MAX_ITER, bp_method="ms", schedule="parallel", ms_scaling_factor=MS_SCALING, want_llr=False)
     if oracle.have_ref():
         ref = oracle.RefOracle()
         sample = int(min(syn_host.shape[0], 8192 * cores))
         syn = np.ascontiguousarray(syn_host[:sample])
         ref.decode_batch(H, syn[: 64 * cores], P_ERR, threads=cores, **kw)
-        t0 = time.perf_counter()
-        ref.decode_batch(H, syn, P_ERR, threads=cores, **kw)
-        dt = time.perf_counter() - t0
+        dt = ref.decode_batch(H, syn, P_ERR, threads=cores, return_seconds=True, **kw)[-1]
         return {"value": sample / dt, "unit": "decodes/s", "cores": cores, "kind": "reference",
-                "sample": f"first {sample} syndromes of the GPU batch, {cores} threads x one reference BpDecoder each"}
+                "sample": f"first {sample} syndromes of the GPU batch, {cores} threads (cgroup cpu quota) x one reference "
+                          f"BpDecoder each, decode loop only"}
     if not oracle.have_port():
         oracle.build()
     port = oracle.PortOracle()

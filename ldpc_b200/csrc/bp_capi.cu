@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "bp_decoder.h"
+#include "bp_smem_params.h"
 #include "bp_stream_params.h"
 
 namespace {
@@ -99,6 +100,8 @@ __global__ void xor_received_kernel(uint8_t *__restrict__ dec, const uint8_t *__
         dec[i] ^= (v[i] != 0);
 }
 
+void build_smem_plan(bpb_decoder *h);
+
 // ---- graph blob ---------------------------------------------------------------------------------------
 
 int upload_graph(bpb_decoder *h) {
@@ -139,6 +142,13 @@ int upload_graph(bpb_decoder *h) {
     if (rc) return rc;
     BPB_CUDA(h, cudaMemcpyAsync(h->order_d.ptr, h->serial_order.data(), h->serial_order.size() * sizeof(uint32_t),
                                 cudaMemcpyHostToDevice, h->stream));
+    build_smem_plan(h);
+    if (h->smem_plan.ok) {
+        rc = ensure(h, h->smem_tab, h->smem_plan.blob.size());
+        if (rc) return rc;
+        BPB_CUDA(h, cudaMemcpyAsync(h->smem_tab.ptr, h->smem_plan.blob.data(), h->smem_plan.blob.size(),
+                                    cudaMemcpyHostToDevice, h->stream));
+    }
     BPB_CUDA(h, cudaStreamSynchronize(h->stream));  // the host vector `blob` dies here
     h->graph_dirty = false;
     return BPB_OK;
@@ -235,6 +245,158 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     return BPB_OK;
 }
 
+// ---- on-chip family: shared-memory plan and launch ------------------------------------------------------
+
+inline uint32_t align_up(uint32_t x, uint32_t q) { return (x + q - 1) / q * q; }
+
+void build_smem_plan(bpb_decoder *h) {
+    const bpb::HostGraph &g = h->g;
+    bpb::SmemPlan &pl = h->smem_plan;
+    pl = bpb::SmemPlan();
+    const int DCm = g.max_row_degree, DVm = g.max_col_degree;
+    const int M = (int) align_up((uint32_t) g.m, 16), N = (int) align_up((uint32_t) g.n, 32);
+    if (DCm > 32 || DVm > 16) {
+        pl.why = "row degree > 32 or column degree > 16";
+        return;
+    }
+    if (DCm < 1 || (int64_t) DCm * M > 65535 || g.n > 65535) {
+        pl.why = "message positions do not fit 16-bit indices";
+        return;
+    }
+    pl.M = M;
+    pl.N = N;
+    uint32_t off = 0;
+    pl.off_row_deg = off;
+    off += (uint32_t) M;
+    pl.off_col_deg = off;
+    off += (uint32_t) N;
+    off = align_up(off, 4);
+    pl.off_row_col = off;
+    off += 2u * (uint32_t) (DCm * M);
+    off = align_up(off, 4);
+    pl.off_col_pos = off;
+    off += 2u * (uint32_t) (DVm * N);
+    off = align_up(off, 8);
+    pl.off_prior = off;
+    if (!h->uniform_prior) off += 8u * (uint32_t) g.n;
+    off = align_up(off, 16);
+    pl.blob.assign(off, 0);
+    uint8_t *row_deg = pl.blob.data() + pl.off_row_deg;
+    uint8_t *col_deg = pl.blob.data() + pl.off_col_deg;
+    uint16_t *row_col = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_row_col);
+    uint16_t *col_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_pos);
+    std::vector<uint32_t> slot_of_edge((size_t) g.nnz);
+    for (int i = 0; i < g.m; i++) {
+        const uint32_t b = g.row_ptr[(size_t) i], e = g.row_ptr[(size_t) i + 1];
+        row_deg[i] = (uint8_t) (e - b);
+        for (uint32_t q = b; q < e; q++) {
+            const uint32_t k = q - b;
+            row_col[(size_t) k * M + i] = (uint16_t) g.col_idx[q];
+            slot_of_edge[q] = k * (uint32_t) M + (uint32_t) i;
+        }
+    }
+    for (int j = 0; j < g.n; j++) {
+        const uint32_t b = g.col_ptr[(size_t) j], e = g.col_ptr[(size_t) j + 1];
+        col_deg[j] = (uint8_t) (e - b);
+        for (uint32_t q = b; q < e; q++) col_pos[(size_t) (q - b) * N + j] = (uint16_t) slot_of_edge[g.csc2csr[q]];
+    }
+    if (!h->uniform_prior) std::memcpy(pl.blob.data() + pl.off_prior, h->prior.data(), 8 * (size_t) g.n);
+    uint32_t go = 0;
+    pl.goff_msg = go;
+    go += 8u * (uint32_t) (DCm * M);
+    pl.goff_dec = go;
+    go += (uint32_t) N;
+    pl.goff_syn = go;
+    go += (uint32_t) M;
+    go = align_up(go, 8);
+    pl.goff_ctl = go;
+    go += 8;
+    pl.group_bytes = align_up(go, 16);
+    if ((size_t) off + pl.group_bytes > (size_t) h->max_smem_optin) {
+        pl.why = "one syndrome's messages do not fit in shared memory";
+        return;
+    }
+    pl.ok = true;
+}
+
+bpb::SmemKernel pick_smem(int method, int dc, int dv, bool llr) {
+    if (method == BPB_MINIMUM_SUM) return bpb::pick_smem_ms(dc, dv, llr);
+    return bpb::pick_smem_ps(dc, dv, llr);
+}
+
+int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
+                int32_t *d_iters, double *d_llr, cudaStream_t st) {
+    const bpb::HostGraph &g = h->g;
+    const bpb::SmemPlan &pl = h->smem_plan;
+    const bool llr = d_llr != nullptr;
+    bpb::SmemKernel k = pick_smem(h->method, g.max_row_degree, g.max_col_degree, llr);
+    if (!k || !pl.ok) {
+        h->err = "on-chip kernel family not available for this code: " + pl.why;
+        return BPB_ERR_UNSUPPORTED;
+    }
+    const int maxt = bpb::smem_cta_threads(h->method, g.max_row_degree, g.max_col_degree);
+    const size_t tab = pl.blob.size();
+    int G = (int) (((size_t) h->max_smem_optin - tab) / pl.group_bytes);
+    G = std::min(G, 15);
+    // threads per group: enough to cover the rows, a multiple of 32, within the CTA budget
+    int T = maxt / G / 32 * 32;
+    if (T < 32) {
+        T = 32;
+        G = maxt / 32;
+    }
+    const int want = std::max(32, (int) align_up((uint32_t) std::max(g.m, (g.n + 1) / 2), 32));
+    T = std::min(T, std::min(want, 256));
+    const int block = G * T;
+    const size_t smem_bytes = tab + (size_t) G * pl.group_bytes;
+    BPB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes));
+    int64_t grid64 = std::min<int64_t>(h->sm_count, (batch + G - 1) / G);
+    if (grid64 < 1) grid64 = 1;
+    int rc;
+    if ((rc = ensure(h, h->counter, 8))) return rc;
+    BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 8, st));
+    bpb::SmemParams p{};
+    p.tab = (const uint32_t *) h->smem_tab.ptr;
+    p.tab_bytes = (uint32_t) tab;
+    p.off_row_deg = pl.off_row_deg;
+    p.off_col_deg = pl.off_col_deg;
+    p.off_row_col = pl.off_row_col;
+    p.off_col_pos = pl.off_col_pos;
+    p.off_prior = pl.off_prior;
+    p.group_bytes = pl.group_bytes;
+    p.goff_msg = pl.goff_msg;
+    p.goff_dec = pl.goff_dec;
+    p.goff_syn = pl.goff_syn;
+    p.goff_ctl = pl.goff_ctl;
+    p.m = g.m;
+    p.n = g.n;
+    p.M = pl.M;
+    p.N = pl.N;
+    p.groups = G;
+    p.T = T;
+    p.max_iter = h->max_iter;
+    p.ms_scaling = h->ms_scaling;
+    p.uniform_prior = h->uniform_prior ? 1 : 0;
+    p.prior0 = h->prior.empty() ? 0.0 : h->prior[0];
+    p.synd_packed = d_packed;
+    p.mwp = mwp;
+    p.batch = batch;
+    p.counter = (unsigned long long *) h->counter.ptr;
+    p.out_dec = d_dec;
+    p.out_conv = d_conv;
+    p.out_iters = d_iters;
+    p.out_llr = d_llr;
+    BPB_CUDA(h, cudaEventRecord(h->kev0, st));
+    k<<<(int) grid64, block, smem_bytes, st>>>(p);
+    BPB_CUDA(h, cudaGetLastError());
+    BPB_CUDA(h, cudaEventRecord(h->kev1, st));
+    h->kernel_timed = true;
+    h->launches += 1;
+    h->last_family = BPB_KERNEL_SMEM;
+    h->last_grid = (int) grid64;
+    h->last_block = block;
+    return BPB_OK;
+}
+
 int check_ready(bpb_decoder *h) {
     if (!h) return BPB_ERR_ARG;
     if (h->channel.empty()) {
@@ -327,7 +489,7 @@ void bpb_destroy(bpb_decoder *h) {
     }
     cudaSetDevice(h->device);
     for (bpb::DeviceBuffer *b: {&h->blob, &h->order_d, &h->counter, &h->msg, &h->dec_w, &h->syn_w, &h->llr_tile,
-                                &h->packed, &h->st_in, &h->st_dec, &h->st_conv, &h->st_iters, &h->st_llr})
+                                &h->packed, &h->smem_tab, &h->st_in, &h->st_dec, &h->st_conv, &h->st_iters, &h->st_llr})
         release(*b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -444,7 +606,18 @@ int bpb_decode_batch_device(bpb_decoder *h, int input_type, const uint8_t *d_inp
     }
     BPB_CUDA(h, cudaGetLastError());
     h->launches += 1;
-    rc = launch_stream(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st);
+    // family: the on-chip kernels serve the parallel schedule of codes whose messages fit in shared memory;
+    // everything else (serial schedule, large codes) streams its messages through HBM.
+    const bool smem_able = h->smem_plan.ok && h->schedule == BPB_PARALLEL;
+    if (h->kernel_pref == BPB_KERNEL_SMEM && !smem_able) {
+        h->err = "kernel family 'smem' requested but not available: " +
+                 (h->schedule != BPB_PARALLEL ? std::string("serial schedule") : h->smem_plan.why);
+        return BPB_ERR_UNSUPPORTED;
+    }
+    if (smem_able && h->kernel_pref != BPB_KERNEL_STREAM)
+        rc = launch_smem(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st);
+    else
+        rc = launch_stream(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st);
     if (rc) return rc;
     if (input_type == BPB_INPUT_RECEIVED_VECTOR) {
         const long long count = (long long) batch * g.n;
@@ -526,8 +699,8 @@ int bpb_get_info(const bpb_decoder *h, bpb_info *out) {
     out->launches = h->launches;
     int64_t ws = 0;
     for (const bpb::DeviceBuffer *b: {&h->blob, &h->order_d, &h->counter, &h->msg, &h->dec_w, &h->syn_w,
-                                      &h->llr_tile, &h->packed, &h->st_in, &h->st_dec, &h->st_conv, &h->st_iters,
-                                      &h->st_llr})
+                                      &h->llr_tile, &h->packed, &h->smem_tab, &h->st_in, &h->st_dec, &h->st_conv,
+                                      &h->st_iters, &h->st_llr})
         ws += (int64_t) b->bytes;
     out->workspace_bytes = ws;
     if (h->kernel_timed) {

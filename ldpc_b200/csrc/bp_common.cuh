@@ -6,14 +6,16 @@
 //   * comparisons are the reference's: `x <= 0` (zero counts as negative, NaN compares false,
 //     reference src_cpp/bp.hpp:240,253,290,513,524) and strict `a < temp` for running minima
 //     (bp.hpp:245,256,266,510);
-//   * tanh is evaluated with the fdlibm formula glibc uses (sysdeps/ieee754/dbl-64/s_tanh.c:
-//     1 - 2/(expm1(2|x|)+2) for 1<=|x|<22, -t/(t+2) with t=expm1(-2|x|) below 1, +-1 above 22) so
-//     that the saturation pattern (where tanh rounds to exactly 1 and the check message becomes
-//     +-inf, bp.hpp:216) is reproduced; only expm1/log differ from glibc, by <= 1 ulp.
+//   * std::tanh and std::log of the product-sum update (bp.hpp:208,216,494,498) are evaluated by
+//     rl_tanh / rl_log (ref_libm.h): the glibc 2.39 algorithms restated operation by operation, so the
+//     product-sum messages -- including where tanh rounds to exactly 1 and the check message becomes
+//     +-inf (bp.hpp:216) -- are the doubles the reference computes on an x86-64 host with FMA.
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
+
+#include "ref_libm.h"
 
 namespace bpb {
 
@@ -22,23 +24,10 @@ constexpr int kMinimumSum = 1;
 constexpr int kSerial = 0;      // reference bp.hpp:28-32
 constexpr int kParallel = 1;
 
-__device__ __forceinline__ double ref_tanh(double x) {
-    const double ax = fabs(x);
-    double z;
-    if (!(ax < 22.0)) {
-        if (ax != ax) return x;  // NaN
-        z = 1.0;                 // |x| >= 22 or inf
-    } else if (ax >= 1.0) {
-        const double t = expm1(2.0 * ax);
-        z = 1.0 - 2.0 / (t + 2.0);
-    } else if (ax < 2.77555756156289135e-17 /* 2^-55 */) {
-        return x * (1.0 + x);
-    } else {
-        const double t = expm1(-2.0 * ax);
-        z = -t / (t + 2.0);
-    }
-    return (x >= 0.0) ? z : -z;  // x = -0.0 handled by the 2^-55 branch
-}
+// Out-of-line on purpose: a product-sum row update makes 2*d_c tanh and d_c log evaluations; inlining every
+// copy bloats the unrolled kernels past the instruction cache (and ptxas takes minutes per kernel).
+__device__ __noinline__ static double ps_tanh_half(double b) { return rl_tanh(b / 2); }   // tanh(b2c / 2), bp.hpp:208
+__device__ __noinline__ static double ps_atanh2(double x) { return rl_log((1 + x) / (1 - x)); }  // bp.hpp:216
 
 // alpha of the min-sum update, reference bp.hpp:222-228 / 459-465
 __device__ __forceinline__ double ms_alpha(double ms_scaling_factor, int it) {

@@ -31,6 +31,16 @@ struct DeviceBuffer {
     size_t bytes = 0;
 };
 
+// Shared-memory plan of the on-chip kernel family (bp_smem.cuh): table blob + per-group areas.
+struct SmemPlan {
+    bool ok = false;
+    std::string why;            // why the family is not usable for this code (when !ok)
+    std::vector<uint8_t> blob;  // tables in their final shared-memory byte layout
+    uint32_t off_row_deg = 0, off_col_deg = 0, off_row_col = 0, off_col_pos = 0, off_prior = 0;
+    uint32_t group_bytes = 0, goff_msg = 0, goff_dec = 0, goff_syn = 0, goff_ctl = 0;
+    int M = 0, N = 0;
+};
+
 }  // namespace bpb
 
 struct bpb_decoder {
@@ -50,7 +60,8 @@ struct bpb_decoder {
     int kernel_pref = BPB_KERNEL_AUTO;
     // device state
     bool graph_dirty = true;  // blob must be (re)uploaded (prior or order changed)
-    bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed;
+    bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed, smem_tab;
+    bpb::SmemPlan smem_plan;
     // staging for the host API
     bpb::DeviceBuffer st_in, st_dec, st_conv, st_iters, st_llr;
     uint32_t blob_words = 0, prior_off = 0;

@@ -1,0 +1,153 @@
+// bp_smem.cuh -- the on-chip kernel family ("one thread group = one syndrome, messages in shared memory").
+//
+// Replaces ldpc::bp::BpDecoder::bp_decode_parallel (reference src_cpp/bp.hpp:192-325) when 8*E bytes of
+// messages fit in shared memory several times over.  The algorithmic HBM traffic of the streaming family
+// (4*E*8 bytes per iteration per syndrome) never leaves the SM here: per syndrome only the
+// packed syndrome comes in and the hard decisions (plus, optionally, the posterior LLRs) go out.
+//
+// One CTA per SM holds ONE copy of the graph tables and G independent thread groups of T threads; each group
+// decodes one syndrome at a time and claims the next from a global counter when it is done (per-syndrome early
+// exit, bp.hpp:300-308).  Groups synchronise only with themselves through named barriers (bar.sync id, T /
+// barrier.red.or for the convergence vote), so a group stuck on a 50-iteration non-converger does not hold up
+// its neighbours.
+//
+// Shared-memory layout of the messages: ELL by rows, msg[k*M + i] = message on the k-th edge (ascending column,
+// the reference's iterate_row order) of check i.  In the check pass thread i owns row i, so for fixed k the
+// lanes of a warp read consecutive doubles (conflict-free); as in the streaming family the update is in
+// place (b2c -> c2b -> b2c).  In the bit pass thread j owns column j and gathers its d_v messages through
+// col_pos[k*N + j] (the only accesses with bank conflicts).  Hard decisions are bytes dec[j]; the candidate
+// syndrome test (bp.hpp:292-300) is a per-row XOR over dec[] followed by an OR-reduction barrier.
+#pragma once
+#include "bp_smem_params.h"
+#include "bp_update.cuh"
+
+namespace bpb {
+
+__device__ __forceinline__ void group_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool group_any(int id, int count, bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(out)
+        : "r"((uint32_t) pred), "r"(id), "r"(count)
+        : "memory");
+    return out != 0;
+}
+
+template <int METHOD, int DC, int DV, bool LLR, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm);
+        for (uint32_t i = threadIdx.x; i < p.tab_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int T = p.T;
+    const int g = threadIdx.x / T;
+    const int t = threadIdx.x - g * T;
+    const int bar = g + 1;  // named barrier of this group (0 is the CTA-wide one used above)
+    const int m = p.m, n = p.n, M = p.M, N = p.N;
+    const uint8_t *row_deg = sm + p.off_row_deg;
+    const uint8_t *col_deg = sm + p.off_col_deg;
+    const uint16_t *row_col = reinterpret_cast<const uint16_t *>(sm + p.off_row_col);
+    const uint16_t *col_pos = reinterpret_cast<const uint16_t *>(sm + p.off_col_pos);
+    const double *prior = reinterpret_cast<const double *>(sm + p.off_prior);
+    uint8_t *garea = sm + p.tab_bytes + (size_t) g * p.group_bytes;
+    double *msg = reinterpret_cast<double *>(garea + p.goff_msg);
+    uint8_t *dec = garea + p.goff_dec;
+    uint8_t *syn = garea + p.goff_syn;
+    volatile long long *ctl = reinterpret_cast<volatile long long *>(garea + p.goff_ctl);
+
+    for (;;) {
+        if (t == 0) ctl[0] = (long long) atomicAdd(p.counter, 1ull);
+        group_sync(bar, T);
+        const long long idx = ctl[0];
+        if (idx >= p.batch) break;
+        // syndrome bits and initialise_log_domain_bp (bp.hpp:147-157)
+        const uint32_t *srow = p.synd_packed + idx * p.mwp;
+        for (int i = t; i < m; i += T) {
+            syn[i] = (uint8_t) ((__ldg(srow + (i >> 5)) >> (i & 31)) & 1u);
+            const int deg = row_deg[i];
+            for (int k = 0; k < deg; ++k)
+                msg[k * M + i] = p.uniform_prior ? p.prior0 : prior[row_col[k * M + i]];
+        }
+        group_sync(bar, T);
+
+        int it = 0;
+        bool conv = false;
+        while (it < p.max_iter) {
+            ++it;
+            const double alpha = ms_alpha(p.ms_scaling, it);
+            // ---- check -> bit, one thread per row (bp.hpp:201-273) ----
+            for (int i = t; i < m; i += T) {
+                const int deg = row_deg[i];
+                double b[DC], c[DC];
+#pragma unroll
+                for (int k = 0; k < DC; ++k) b[k] = (k < deg) ? msg[k * M + i] : 0.0;
+                check_node_update<METHOD, DC>(b, deg, (uint32_t) syn[i], alpha, c);
+#pragma unroll
+                for (int k = 0; k < DC; ++k)
+                    if (k < deg) msg[k * M + i] = c[k];
+            }
+            group_sync(bar, T);
+            // ---- posterior, decision, bit -> check, one thread per column (bp.hpp:276-318) ----
+            for (int j = t; j < n; j += T) {
+                const int deg = col_deg[j];
+                uint32_t pos[DV];
+                double c[DV];
+#pragma unroll
+                for (int k = 0; k < DV; ++k) pos[k] = (k < deg) ? col_pos[k * N + j] : 0u;
+#pragma unroll
+                for (int k = 0; k < DV; ++k) c[k] = (k < deg) ? msg[pos[k]] : 0.0;
+                const double llr = bit_node_update<DV>(c, deg, p.uniform_prior ? p.prior0 : prior[j]);
+#pragma unroll
+                for (int k = 0; k < DV; ++k)
+                    if (k < deg) msg[pos[k]] = c[k];
+                dec[j] = (llr <= 0) ? 1 : 0;
+                if (LLR) p.out_llr[idx * n + j] = llr;
+            }
+            group_sync(bar, T);
+            // ---- candidate syndrome == syndrome ?  (bp.hpp:292-308) ----
+            uint32_t bad = 0;
+            for (int i = t; i < m; i += T) {
+                const int deg = row_deg[i];
+                uint32_t par = syn[i];
+                for (int k = 0; k < deg; ++k) par ^= dec[row_col[k * M + i]];
+                bad |= par;
+            }
+            conv = !group_any(bar, T, bad != 0);
+            if (conv) break;
+        }
+        // ---- retire ----
+        uint8_t *drow = p.out_dec + idx * n;
+        if ((n & 3) == 0) {
+            const uint32_t *d32 = reinterpret_cast<const uint32_t *>(dec);
+            uint32_t *o32 = reinterpret_cast<uint32_t *>(drow);
+            for (int w = t; w < (n >> 2); w += T) o32[w] = d32[w];
+        } else {
+            for (int j = t; j < n; j += T) drow[j] = dec[j];
+        }
+        if (t == 0) {
+            if (p.out_iters) p.out_iters[idx] = it;
+            if (p.out_conv) p.out_conv[idx] = conv ? 1 : 0;
+        }
+    }
+}
+
+template <int METHOD>
+SmemKernel pick_smem_bucket(int dc, int dv, bool llr) {
+#define BPB_PICK(DC_, DV_, MAXT_) \
+    return llr ? bp_smem_kernel<METHOD, DC_, DV_, true, MAXT_> : bp_smem_kernel<METHOD, DC_, DV_, false, MAXT_>
+    constexpr int SMALL = (METHOD == kMinimumSum) ? 1024 : 512;  // must agree with smem_cta_threads()
+    if (dc <= 8 && dv <= 4) { BPB_PICK(8, 4, SMALL); }
+    if (dc <= 8 && dv <= 16) { BPB_PICK(8, 16, 512); }
+    if (dc <= 32 && dv <= 4) { BPB_PICK(32, 4, 512); }
+    if (dc <= 32 && dv <= 16) { BPB_PICK(32, 16, 512); }
+#undef BPB_PICK
+    return nullptr;
+}
+
+}  // namespace bpb

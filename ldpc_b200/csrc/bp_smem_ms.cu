@@ -1,0 +1,5 @@
+// Instantiates the min-sum on-chip kernels (bp_smem.cuh) for every degree bucket; 1024 threads per CTA.
+#include "bp_smem.cuh"
+namespace bpb {
+SmemKernel pick_smem_ms(int dc, int dv, bool llr) { return pick_smem_bucket<kMinimumSum>(dc, dv, llr); }
+}  // namespace bpb

@@ -1,0 +1,39 @@
+// bp_smem_params.h -- launch parameters of the on-chip kernel family (see bp_smem.cuh).
+#pragma once
+#include <stdint.h>
+
+namespace bpb {
+
+struct SmemParams {
+    const uint32_t *tab;  // table blob in global memory, copied verbatim to the start of shared memory
+    uint32_t tab_bytes;   // multiple of 16
+    uint32_t off_row_deg, off_col_deg, off_row_col, off_col_pos, off_prior;  // byte offsets inside the blob
+    uint32_t group_bytes;                                                    // per-group area (multiple of 16)
+    uint32_t goff_msg, goff_dec, goff_syn, goff_ctl;                         // byte offsets inside a group area
+    int m, n, M, N;       // M, N: padded row / column counts (ELL strides)
+    int groups, T;        // thread groups per CTA, threads per group
+    int max_iter;
+    double ms_scaling;
+    int uniform_prior;
+    double prior0;
+    const uint32_t *synd_packed;  // [B][mwp]
+    int mwp;
+    long long batch;
+    unsigned long long *counter;
+    uint8_t *out_dec;     // [B][n]
+    uint8_t *out_conv;    // [B] or null
+    int32_t *out_iters;   // [B] or null
+    double *out_llr;      // [B][n] or null
+};
+
+using SmemKernel = void (*)(const SmemParams);
+
+// CTA size the kernels are compiled for (__launch_bounds__): 1024 threads (64 registers each) only for the small
+// min-sum bucket, 512 (128 registers) otherwise.
+inline int smem_cta_threads(int method, int dc, int dv) { return (method == 1 && dc <= 8 && dv <= 4) ? 1024 : 512; }
+
+// defined in bp_smem_{ms,ps}.cu; nullptr when no degree bucket fits
+SmemKernel pick_smem_ms(int max_row_degree, int max_col_degree, bool llr);
+SmemKernel pick_smem_ps(int max_row_degree, int max_col_degree, bool llr);
+
+}  // namespace bpb

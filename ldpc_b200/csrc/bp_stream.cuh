@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
 #pragma unroll
                         for (int k = 0; k < DC; ++k) {
                             if (k < deg[r]) {
-                                t[k] = ref_tanh(b[r][k] / 2);
+                                t[k] = ps_tanh_half(b[r][k]);
                                 c[k] = pre;
                                 pre *= t[k];
                             }
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
                         for (int k = DC - 1; k >= 0; --k) {
                             if (k < deg[r]) {
                                 const double x = c[k] * suf;
-                                c[k] = sigma * log((1 + x) / (1 - x));
+                                c[k] = sigma * ps_atanh2(x);
                                 suf *= t[k];
                             }
                         }
@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
                             double x = 1.0;
 #pragma unroll
                             for (int f = 0; f < DC; ++f)
-                                if (f < rdeg && rbeg + f != e) x *= ref_tanh(bv[f] / 2);
-                            c[k] = (s ? -1.0 : 1.0) * log((1 + x) / (1 - x));
+                                if (f < rdeg && rbeg + f != e) x *= ps_tanh_half(bv[f]);
+                            c[k] = (s ? -1.0 : 1.0) * ps_atanh2(x);
                         }
                     }
                 }

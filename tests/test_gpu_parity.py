@@ -10,8 +10,13 @@ from util import assert_same_decode
 pytestmark = pytest.mark.gpu
 
 
-def _decode_gpu(H, syn, p, **kw):
-    dec = BpDecoder(H, error_channel=np.broadcast_to(np.asarray(p, float), (H.shape[1],)).copy(),
+FAMILIES = ["stream", "smem"]
+
+
+def _decode_gpu(H, syn, p, kernel="auto", **kw):
+    if kernel == "smem" and kw.get("schedule", "parallel") not in ("parallel", "p", 0):
+        pytest.skip("the on-chip family implements the parallel schedule")
+    dec = BpDecoder(H, kernel=kernel, error_channel=np.broadcast_to(np.asarray(p, float), (H.shape[1],)).copy(),
                     input_vector_type="syndrome", **kw)
     out = dec.decode_batch(syn, return_llr=True)
     return out, dec.converge_batch, dec.iter_batch, dec.log_prob_ratios_batch
@@ -25,7 +30,8 @@ def H1000():
 @pytest.mark.parametrize("method", ["ms", "ps"])
 @pytest.mark.parametrize("schedule", ["parallel", "serial"])
 @pytest.mark.parametrize("ms_scaling", [0.625, 0.0, 1.0])
-def test_regular_n1000(port_oracle, H1000, method, schedule, ms_scaling):
+@pytest.mark.parametrize("kernel", FAMILIES)
+def test_regular_n1000(port_oracle, H1000, method, schedule, ms_scaling, kernel):
     if method == "ps" and ms_scaling != 0.625:
         pytest.skip("ms_scaling_factor is unused by product_sum")
     B = 1536 if method == "ms" else 512
@@ -33,28 +39,31 @@ def test_regular_n1000(port_oracle, H1000, method, schedule, ms_scaling):
                           codes.bsc_syndromes(H1000, 0.09, B // 8, seed=8)])  # the second part mostly fails
     kw = dict(max_iter=50, bp_method=method, schedule=schedule, ms_scaling_factor=ms_scaling)
     want = port_oracle.decode_batch(H1000, syn, 0.05, **kw)
-    got = _decode_gpu(H1000, syn, 0.05, **kw)
+    got = _decode_gpu(H1000, syn, 0.05, kernel=kernel, **kw)
     assert_same_decode(got, want, llr_exact=(method == "ms"))
     assert 0 < want[1].mean() < 1  # both convergers and non-convergers are covered
 
 
-def test_surface_d13_product_sum(port_oracle):
+@pytest.mark.parametrize("kernel", FAMILIES)
+def test_surface_d13_product_sum(port_oracle, kernel):
     H = codes.rotated_surface_code_x(13)
     syn = codes.bsc_syndromes(H, 0.05, 4096, seed=3)
     kw = dict(max_iter=30, bp_method="ps", schedule="parallel")
-    assert_same_decode(_decode_gpu(H, syn, 0.05, **kw), port_oracle.decode_batch(H, syn, 0.05, **kw))
+    assert_same_decode(_decode_gpu(H, syn, 0.05, kernel=kernel, **kw), port_oracle.decode_batch(H, syn, 0.05, **kw))
 
 
-def test_hamming5_readme_config(port_oracle):
+@pytest.mark.parametrize("kernel", FAMILIES)
+def test_hamming5_readme_config(port_oracle, kernel):
     H = codes.hamming_code(5)
     rng = np.random.default_rng(0)
     syn = rng.integers(0, 2, size=(100, 5)).astype(np.uint8)
     kw = dict(max_iter=2, bp_method="product_sum", schedule="parallel")
-    assert_same_decode(_decode_gpu(H, syn, 0.1, **kw), port_oracle.decode_batch(H, syn, 0.1, **kw))
+    assert_same_decode(_decode_gpu(H, syn, 0.1, kernel=kernel, **kw), port_oracle.decode_batch(H, syn, 0.1, **kw))
 
 
 @pytest.mark.parametrize("method", ["ms", "ps"])
-def test_nonuniform_channel_with_certain_bits(port_oracle, method):
+@pytest.mark.parametrize("kernel", FAMILIES)
+def test_nonuniform_channel_with_certain_bits(port_oracle, method, kernel):
     """error_channel with p = 0 entries gives infinite priors (reference python_test/test_bp_decoder.py:188-192)."""
     H = codes.regular_ldpc(120, 3, 6, seed=5)
     rng = np.random.default_rng(11)
@@ -64,7 +73,7 @@ def test_nonuniform_channel_with_certain_bits(port_oracle, method):
     syn = codes.syndromes_of(H, err)
     kw = dict(max_iter=20, bp_method=method, schedule="parallel", ms_scaling_factor=0.75)
     want = port_oracle.decode_batch(H, syn, p, **kw)
-    assert_same_decode(_decode_gpu(H, syn, p, **kw), want, llr_exact=(method == "ms"))
+    assert_same_decode(_decode_gpu(H, syn, p, kernel=kernel, **kw), want, llr_exact=(method == "ms"))
     assert np.isinf(want[3]).any()
 
 
@@ -79,7 +88,8 @@ def test_custom_serial_order(port_oracle):
         assert_same_decode(got, want, llr_exact=(method == "ms"))
 
 
-def test_irregular_degrees(port_oracle):
+@pytest.mark.parametrize("kernel", FAMILIES)
+def test_irregular_degrees(port_oracle, kernel):
     """Row degrees 1..~12 and column degrees 1..~9: exercises the larger degree buckets and degree-1 rows
     (magnitude DBL_MAX * alpha)."""
     rng = np.random.default_rng(21)
@@ -94,8 +104,10 @@ def test_irregular_degrees(port_oracle):
     syn = codes.syndromes_of(H, err)
     for method, sched in (("ms", "parallel"), ("ps", "parallel"), ("ms", "serial"), ("ps", "serial")):
         kw = dict(max_iter=15, bp_method=method, schedule=sched, ms_scaling_factor=0.625)
+        if kernel == "smem" and sched == "serial":
+            continue
         want = port_oracle.decode_batch(H, syn, 0.04, **kw)
-        assert_same_decode(_decode_gpu(H, syn, 0.04, **kw), want, llr_exact=(method == "ms"))
+        assert_same_decode(_decode_gpu(H, syn, 0.04, kernel=kernel, **kw), want, llr_exact=(method == "ms"))
 
 
 def test_received_vector_input(port_oracle):
@@ -124,14 +136,15 @@ def test_bposd_bb144(port_oracle):
     assert np.array_equal(codes.syndromes_of(H, got), syn)
 
 
-def test_full_size_round_trip(H1000):
+@pytest.mark.parametrize("kernel", FAMILIES)
+def test_full_size_round_trip(H1000, kernel):
     """BASELINE config 2 at full size (2^20 syndromes, min-sum 50 iterations): size-independent properties.
     Every converged row reproduces its syndrome; iteration counts are in range; the statistics match the
     oracle's on this code (~99.3 % convergence, ~8.3 mean iterations)."""
     B = 1 << 20
     syn = codes.bsc_syndromes(H1000, 0.05, B, seed=7)
     d = BpDecoder(H1000, error_rate=0.05, max_iter=50, bp_method="ms", ms_scaling_factor=0.625,
-                  input_vector_type="syndrome")
+                  input_vector_type="syndrome", kernel=kernel)
     dec = d.decode_batch(syn)
     conv, its = d.converge_batch, d.iter_batch
     assert dec.shape == (B, 1000) and dec.max() <= 1
@@ -148,7 +161,8 @@ def test_full_size_round_trip(H1000):
     assert np.array_equal(d.iter_batch, its[perm])
 
 
-def test_golden_fixtures_from_reference():
+@pytest.mark.parametrize("kernel", FAMILIES)
+def test_golden_fixtures_from_reference(kernel):
     """tests/golden/*.npz were produced by the unmodified reference C++ (tests/golden/make_golden.py)."""
     import glob
     import os
@@ -160,6 +174,8 @@ def test_golden_fixtures_from_reference():
         H = sp.csr_matrix((np.ones(z["rows"].size, np.uint8), (z["rows"], z["cols"])), shape=tuple(z["shape"]))
         kw = dict(max_iter=int(z["max_iter"]), bp_method=str(z["bp_method"]), schedule=str(z["schedule"]),
                   ms_scaling_factor=float(z["ms_scaling_factor"]))
-        got = _decode_gpu(H, z["syndromes"], z["channel"], **kw)
+        if kernel == "smem" and kw["schedule"] != "parallel":
+            continue
+        got = _decode_gpu(H, z["syndromes"], z["channel"], kernel=kernel, **kw)
         assert_same_decode(got, (z["decoding"], z["converged"], z["iters"], z["llr"]),
                            llr_exact=(str(z["bp_method"]) == "ms"))
