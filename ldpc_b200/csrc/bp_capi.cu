@@ -45,6 +45,12 @@ int ensure(bpb_decoder *h, bpb::DeviceBuffer &b, size_t bytes, bool zero = false
     return BPB_OK;
 }
 
+std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
+    return {&h->blob,     &h->order_d,   &h->counter,   &h->msg,        &h->dec_w,      &h->syn_w,    &h->llr_tile,
+            &h->packed,   &h->smem_tab,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
+            &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1]};
+}
+
 void release(bpb::DeviceBuffer &b) {
     if (b.ptr) cudaFree(b.ptr);
     b.ptr = nullptr;
@@ -305,7 +311,7 @@ void build_smem_plan(bpb_decoder *h) {
     pl.goff_msg = go;
     go += 8u * (uint32_t) (DCm * M);
     pl.goff_dec = go;
-    go += (uint32_t) N;
+    go += (uint32_t) N / 8;  // one bit per column
     pl.goff_syn = go;
     go += (uint32_t) M;
     go = align_up(go, 8);
@@ -319,9 +325,9 @@ void build_smem_plan(bpb_decoder *h) {
     pl.ok = true;
 }
 
-bpb::SmemKernel pick_smem(int method, int dc, int dv, bool llr) {
-    if (method == BPB_MINIMUM_SUM) return bpb::pick_smem_ms(dc, dv, llr);
-    return bpb::pick_smem_ps(dc, dv, llr);
+bpb::SmemKernel pick_smem(int method, int dc, int dv, bool regular, bool llr) {
+    if (method == BPB_MINIMUM_SUM) return bpb::pick_smem_ms(dc, dv, regular, llr);
+    return bpb::pick_smem_ps(dc, dv, regular, llr);
 }
 
 int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
@@ -329,7 +335,7 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     const bpb::HostGraph &g = h->g;
     const bpb::SmemPlan &pl = h->smem_plan;
     const bool llr = d_llr != nullptr;
-    bpb::SmemKernel k = pick_smem(h->method, g.max_row_degree, g.max_col_degree, llr);
+    bpb::SmemKernel k = pick_smem(h->method, g.max_row_degree, g.max_col_degree, g.regular, llr);
     if (!k || !pl.ok) {
         h->err = "on-chip kernel family not available for this code: " + pl.why;
         return BPB_ERR_UNSUPPORTED;
@@ -468,6 +474,13 @@ int bpb_create(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *co
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&h->kev0);
@@ -488,9 +501,14 @@ void bpb_destroy(bpb_decoder *h) {
         return;
     }
     cudaSetDevice(h->device);
-    for (bpb::DeviceBuffer *b: {&h->blob, &h->order_d, &h->counter, &h->msg, &h->dec_w, &h->syn_w, &h->llr_tile,
-                                &h->packed, &h->smem_tab, &h->st_in, &h->st_dec, &h->st_conv, &h->st_iters, &h->st_llr})
-        release(*b);
+    for (bpb::DeviceBuffer *b: all_buffers(h)) release(*b);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->kev0) cudaEventDestroy(h->kev0);
@@ -639,35 +657,52 @@ int bpb_decode_batch(bpb_decoder *h, int input_type, const uint8_t *input, int64
     }
     if (batch == 0) return BPB_OK;
     BPB_CUDA(h, cudaSetDevice(h->device));
+    if (h->graph_dirty && (rc = upload_graph(h))) return rc;
     const bpb::HostGraph &g = h->g;
     const int in_w = (input_type == BPB_INPUT_RECEIVED_VECTOR) ? g.n : g.m;
-    const int64_t chunk_max = (int64_t) 1 << 20;
-    for (int64_t lo = 0; lo < batch; lo += chunk_max) {
+    // Chunked three-stage pipeline (H2D | kernels | D2H) over two staging slots.  The on-chip family keeps no
+    // per-lane state in HBM, so small chunks cost nothing; the streaming family amortises its persistent-lane
+    // ramp-down over large chunks.
+    const bool smem_able = h->smem_plan.ok && h->schedule == BPB_PARALLEL && h->kernel_pref != BPB_KERNEL_STREAM;
+    const int64_t chunk_max = smem_able ? ((int64_t) 1 << 17) : ((int64_t) 1 << 20);
+    int64_t c = 0;
+    for (int64_t lo = 0; lo < batch; lo += chunk_max, ++c) {
+        const int s = (int) (c & 1);
         const int64_t nb = std::min(chunk_max, batch - lo);
-        if ((rc = ensure(h, h->st_in, (size_t) nb * in_w))) return rc;
-        if ((rc = ensure(h, h->st_dec, (size_t) nb * g.n))) return rc;
-        if ((rc = ensure(h, h->st_conv, (size_t) nb))) return rc;
-        if ((rc = ensure(h, h->st_iters, (size_t) nb * 4))) return rc;
-        if (llr && (rc = ensure(h, h->st_llr, (size_t) nb * g.n * 8))) return rc;
-        BPB_CUDA(h, cudaMemcpyAsync(h->st_in.ptr, input + lo * in_w, (size_t) nb * in_w, cudaMemcpyHostToDevice,
-                                    h->stream));
-        rc = bpb_decode_batch_device(h, input_type, (const uint8_t *) h->st_in.ptr, nb, (uint8_t *) h->st_dec.ptr,
-                                     (uint8_t *) h->st_conv.ptr, (int32_t *) h->st_iters.ptr,
-                                     llr ? (double *) h->st_llr.ptr : nullptr, h->stream);
+        const size_t cap = (size_t) std::min(chunk_max, batch);
+        if ((rc = ensure(h, h->st_in[s], cap * in_w))) return rc;
+        if ((rc = ensure(h, h->st_dec[s], cap * g.n))) return rc;
+        if ((rc = ensure(h, h->st_conv[s], cap))) return rc;
+        if ((rc = ensure(h, h->st_iters[s], cap * 4))) return rc;
+        if (llr && (rc = ensure(h, h->st_llr[s], cap * g.n * 8))) return rc;
+        if (c >= 2) BPB_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_k[s], 0));  // slot's input consumed
+        BPB_CUDA(h, cudaMemcpyAsync(h->st_in[s].ptr, input + lo * in_w, (size_t) nb * in_w, cudaMemcpyHostToDevice,
+                                    h->s_in));
+        BPB_CUDA(h, cudaEventRecord(h->ev_in[s], h->s_in));
+        BPB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
+        if (c >= 2) BPB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_out[s], 0));  // slot's outputs drained
+        rc = bpb_decode_batch_device(h, input_type, (const uint8_t *) h->st_in[s].ptr, nb,
+                                     (uint8_t *) h->st_dec[s].ptr, (uint8_t *) h->st_conv[s].ptr,
+                                     (int32_t *) h->st_iters[s].ptr, llr ? (double *) h->st_llr[s].ptr : nullptr,
+                                     h->stream);
         if (rc) return rc;
-        BPB_CUDA(h, cudaMemcpyAsync(decoding + lo * g.n, h->st_dec.ptr, (size_t) nb * g.n, cudaMemcpyDeviceToHost,
-                                    h->stream));
+        BPB_CUDA(h, cudaEventRecord(h->ev_k[s], h->stream));
+        BPB_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_k[s], 0));
+        BPB_CUDA(h, cudaMemcpyAsync(decoding + lo * g.n, h->st_dec[s].ptr, (size_t) nb * g.n, cudaMemcpyDeviceToHost,
+                                    h->s_out));
         if (converged)
-            BPB_CUDA(h, cudaMemcpyAsync(converged + lo, h->st_conv.ptr, (size_t) nb, cudaMemcpyDeviceToHost,
-                                        h->stream));
+            BPB_CUDA(h, cudaMemcpyAsync(converged + lo, h->st_conv[s].ptr, (size_t) nb, cudaMemcpyDeviceToHost,
+                                        h->s_out));
         if (iterations)
-            BPB_CUDA(h, cudaMemcpyAsync(iterations + lo, h->st_iters.ptr, (size_t) nb * 4, cudaMemcpyDeviceToHost,
-                                        h->stream));
+            BPB_CUDA(h, cudaMemcpyAsync(iterations + lo, h->st_iters[s].ptr, (size_t) nb * 4,
+                                        cudaMemcpyDeviceToHost, h->s_out));
         if (llr)
-            BPB_CUDA(h, cudaMemcpyAsync(llr + lo * g.n, h->st_llr.ptr, (size_t) nb * g.n * 8,
-                                        cudaMemcpyDeviceToHost, h->stream));
-        BPB_CUDA(h, cudaStreamSynchronize(h->stream));
+            BPB_CUDA(h, cudaMemcpyAsync(llr + lo * g.n, h->st_llr[s].ptr, (size_t) nb * g.n * 8,
+                                        cudaMemcpyDeviceToHost, h->s_out));
+        BPB_CUDA(h, cudaEventRecord(h->ev_out[s], h->s_out));
     }
+    BPB_CUDA(h, cudaStreamSynchronize(h->s_out));
+    BPB_CUDA(h, cudaStreamSynchronize(h->stream));
     return BPB_OK;
 }
 
@@ -698,10 +733,7 @@ int bpb_get_info(const bpb_decoder *h, bpb_info *out) {
     out->block = h->last_block;
     out->launches = h->launches;
     int64_t ws = 0;
-    for (const bpb::DeviceBuffer *b: {&h->blob, &h->order_d, &h->counter, &h->msg, &h->dec_w, &h->syn_w,
-                                      &h->llr_tile, &h->packed, &h->smem_tab, &h->st_in, &h->st_dec, &h->st_conv,
-                                      &h->st_iters, &h->st_llr})
-        ws += (int64_t) b->bytes;
+    for (bpb::DeviceBuffer *b: all_buffers(const_cast<bpb_decoder *>(h))) ws += (int64_t) b->bytes;
     out->workspace_bytes = ws;
     if (h->kernel_timed) {
         // CUDA-event time of the most recent message-update kernel (valid once that launch has finished)

@@ -17,6 +17,7 @@ struct HostGraph {
     std::vector<uint32_t> row_ptr, col_idx;            // CSR
     std::vector<uint32_t> col_ptr, row_idx, csc2csr;   // CSC; csc2csr: CSC position -> CSR edge id
     int max_row_degree = 0, max_col_degree = 0;
+    bool regular = false;  // every row has max_row_degree entries and every column max_col_degree
 };
 
 int build_host_graph(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *cols, HostGraph &g,
@@ -63,7 +64,9 @@ struct bpb_decoder {
     bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed, smem_tab;
     bpb::SmemPlan smem_plan;
     // staging for the host API
-    bpb::DeviceBuffer st_in, st_dec, st_conv, st_iters, st_llr;
+    bpb::DeviceBuffer st_in[2], st_dec[2], st_conv[2], st_iters[2], st_llr[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host API pipeline
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     uint32_t blob_words = 0, prior_off = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr;

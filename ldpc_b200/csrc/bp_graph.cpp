@@ -52,6 +52,11 @@ int build_host_graph(int m, int n, int64_t nnz, const int32_t *rows, const int32
         g.max_col_degree = std::max(g.max_col_degree, (int) g.col_ptr[(size_t) j + 1]);
         g.col_ptr[(size_t) j + 1] += g.col_ptr[(size_t) j];
     }
+    g.regular = g.nnz > 0;
+    for (int i = 0; i < m && g.regular; i++)
+        if ((int) (g.row_ptr[(size_t) i + 1] - g.row_ptr[(size_t) i]) != g.max_row_degree) g.regular = false;
+    for (int j = 0; j < n && g.regular; j++)
+        if ((int) (g.col_ptr[(size_t) j + 1] - g.col_ptr[(size_t) j]) != g.max_col_degree) g.regular = false;
     std::vector<uint32_t> fill((size_t) n, 0u);
     for (size_t e = 0; e < key.size(); e++) {  // ascending row order => each column receives ascending rows
         const int r = (int) (key[e] / n), c = (int) (key[e] % n);

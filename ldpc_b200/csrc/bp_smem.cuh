@@ -15,8 +15,9 @@
 // the reference's iterate_row order) of check i.  In the check pass thread i owns row i, so for fixed k the
 // lanes of a warp read consecutive doubles (conflict-free); as in the streaming family the update is in
 // place (b2c -> c2b -> b2c).  In the bit pass thread j owns column j and gathers its d_v messages through
-// col_pos[k*N + j] (the only accesses with bank conflicts).  Hard decisions are bytes dec[j]; the candidate
-// syndrome test (bp.hpp:292-300) is a per-row XOR over dec[] followed by an OR-reduction barrier.
+// col_pos[k*N + j] (the only accesses with bank conflicts).  Hard decisions are ballot words (one bit per column,
+// n <= 1024 bits sit in 32 different banks so the per-row gathers are conflict-free); the candidate syndrome
+// test (bp.hpp:292-300) is a per-row XOR over those bits followed by an OR-reduction barrier.
 #pragma once
 #include "bp_smem_params.h"
 #include "bp_update.cuh"
@@ -36,7 +37,9 @@ __device__ __forceinline__ bool group_any(int id, int count, bool pred) {
     return out != 0;
 }
 
-template <int METHOD, int DC, int DV, bool LLR, int MAXT>
+// UNI: every row has exactly DC entries and every column exactly DV (regular codes): no degree tables, no
+// predication.  Otherwise DC / DV are upper bounds and each slot is predicated on the actual degree.
+template <int METHOD, int DC, int DV, bool LLR, int MAXT, bool UNI>
 __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
     extern __shared__ __align__(16) uint8_t sm[];
     {
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
     const double *prior = reinterpret_cast<const double *>(sm + p.off_prior);
     uint8_t *garea = sm + p.tab_bytes + (size_t) g * p.group_bytes;
     double *msg = reinterpret_cast<double *>(garea + p.goff_msg);
-    uint8_t *dec = garea + p.goff_dec;
+    uint32_t *dec = reinterpret_cast<uint32_t *>(garea + p.goff_dec);  // hard decisions, one bit per column
     uint8_t *syn = garea + p.goff_syn;
     volatile long long *ctl = reinterpret_cast<volatile long long *>(garea + p.goff_ctl);
 
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
         const uint32_t *srow = p.synd_packed + idx * p.mwp;
         for (int i = t; i < m; i += T) {
             syn[i] = (uint8_t) ((__ldg(srow + (i >> 5)) >> (i & 31)) & 1u);
-            const int deg = row_deg[i];
+            const int deg = UNI ? DC : row_deg[i];
             for (int k = 0; k < deg; ++k)
                 msg[k * M + i] = p.uniform_prior ? p.prior0 : prior[row_col[k * M + i]];
         }
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
             const double alpha = ms_alpha(p.ms_scaling, it);
             // ---- check -> bit, one thread per row (bp.hpp:201-273) ----
             for (int i = t; i < m; i += T) {
-                const int deg = row_deg[i];
+                const int deg = UNI ? DC : row_deg[i];
                 double b[DC], c[DC];
 #pragma unroll
                 for (int k = 0; k < DC; ++k) b[k] = (k < deg) ? msg[k * M + i] : 0.0;
@@ -94,29 +97,48 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
             }
             group_sync(bar, T);
             // ---- posterior, decision, bit -> check, one thread per column (bp.hpp:276-318) ----
-            for (int j = t; j < n; j += T) {
-                const int deg = col_deg[j];
-                uint32_t pos[DV];
-                double c[DV];
+            for (int j0 = 0; j0 < N; j0 += T) {  // N is a multiple of 32: whole warps are in or out
+                const int j = j0 + t;
+                bool x = false;
+                if (j < n) {
+                    const int deg = UNI ? DV : col_deg[j];
+                    uint32_t pos[DV];
+                    double c[DV];
 #pragma unroll
-                for (int k = 0; k < DV; ++k) pos[k] = (k < deg) ? col_pos[k * N + j] : 0u;
+                    for (int k = 0; k < DV; ++k) pos[k] = (k < deg) ? col_pos[k * N + j] : 0u;
 #pragma unroll
-                for (int k = 0; k < DV; ++k) c[k] = (k < deg) ? msg[pos[k]] : 0.0;
-                const double llr = bit_node_update<DV>(c, deg, p.uniform_prior ? p.prior0 : prior[j]);
+                    for (int k = 0; k < DV; ++k) c[k] = (k < deg) ? msg[pos[k]] : 0.0;
+                    const double llr = bit_node_update<DV>(c, deg, p.uniform_prior ? p.prior0 : prior[j]);
 #pragma unroll
-                for (int k = 0; k < DV; ++k)
-                    if (k < deg) msg[pos[k]] = c[k];
-                dec[j] = (llr <= 0) ? 1 : 0;
-                if (LLR) p.out_llr[idx * n + j] = llr;
+                    for (int k = 0; k < DV; ++k)
+                        if (k < deg) msg[pos[k]] = c[k];
+                    x = (llr <= 0);
+                    if (LLR) p.out_llr[idx * n + j] = llr;
+                }
+                if (j0 + (t & ~31) < N) {
+                    const uint32_t word = __ballot_sync(0xffffffffu, x);
+                    if ((t & 31) == 0) dec[j >> 5] = word;
+                }
             }
             group_sync(bar, T);
             // ---- candidate syndrome == syndrome ?  (bp.hpp:292-308) ----
             uint32_t bad = 0;
             for (int i = t; i < m; i += T) {
-                const int deg = row_deg[i];
                 uint32_t par = syn[i];
-                for (int k = 0; k < deg; ++k) par ^= dec[row_col[k * M + i]];
-                bad |= par;
+                if (UNI) {
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) {
+                        const uint32_t cj = row_col[k * M + i];
+                        par ^= dec[cj >> 5] >> (cj & 31);
+                    }
+                } else {
+                    const int deg = row_deg[i];
+                    for (int k = 0; k < deg; ++k) {
+                        const uint32_t cj = row_col[k * M + i];
+                        par ^= dec[cj >> 5] >> (cj & 31);
+                    }
+                }
+                bad |= par & 1u;
             }
             conv = !group_any(bar, T, bad != 0);
             if (conv) break;
@@ -124,11 +146,13 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
         // ---- retire ----
         uint8_t *drow = p.out_dec + idx * n;
         if ((n & 3) == 0) {
-            const uint32_t *d32 = reinterpret_cast<const uint32_t *>(dec);
             uint32_t *o32 = reinterpret_cast<uint32_t *>(drow);
-            for (int w = t; w < (n >> 2); w += T) o32[w] = d32[w];
+            for (int w = t; w < (n >> 2); w += T) {
+                const uint32_t bits = dec[w >> 3] >> ((w & 7) * 4);
+                o32[w] = (bits & 1u) | ((bits & 2u) << 7) | ((bits & 4u) << 14) | ((bits & 8u) << 21);
+            }
         } else {
-            for (int j = t; j < n; j += T) drow[j] = dec[j];
+            for (int j = t; j < n; j += T) drow[j] = (uint8_t) ((dec[j >> 5] >> (j & 31)) & 1u);
         }
         if (t == 0) {
             if (p.out_iters) p.out_iters[idx] = it;
@@ -138,14 +162,16 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
 }
 
 template <int METHOD>
-SmemKernel pick_smem_bucket(int dc, int dv, bool llr) {
-#define BPB_PICK(DC_, DV_, MAXT_) \
-    return llr ? bp_smem_kernel<METHOD, DC_, DV_, true, MAXT_> : bp_smem_kernel<METHOD, DC_, DV_, false, MAXT_>
+SmemKernel pick_smem_bucket(int dc, int dv, bool regular, bool llr) {
+#define BPB_PICK(DC_, DV_, MAXT_, UNI_)                                 \
+    return llr ? bp_smem_kernel<METHOD, DC_, DV_, true, MAXT_, UNI_>    \
+               : bp_smem_kernel<METHOD, DC_, DV_, false, MAXT_, UNI_>
     constexpr int SMALL = (METHOD == kMinimumSum) ? 1024 : 512;  // must agree with smem_cta_threads()
-    if (dc <= 8 && dv <= 4) { BPB_PICK(8, 4, SMALL); }
-    if (dc <= 8 && dv <= 16) { BPB_PICK(8, 16, 512); }
-    if (dc <= 32 && dv <= 4) { BPB_PICK(32, 4, 512); }
-    if (dc <= 32 && dv <= 16) { BPB_PICK(32, 16, 512); }
+    if (regular && dc == 6 && dv == 3) { BPB_PICK(6, 3, SMALL, true); }  // (3,6)-regular LDPC, bivariate bicycle
+    if (dc <= 8 && dv <= 4) { BPB_PICK(8, 4, SMALL, false); }
+    if (dc <= 8 && dv <= 16) { BPB_PICK(8, 16, 512, false); }
+    if (dc <= 32 && dv <= 4) { BPB_PICK(32, 4, 512, false); }
+    if (dc <= 32 && dv <= 16) { BPB_PICK(32, 16, 512, false); }
 #undef BPB_PICK
     return nullptr;
 }

@@ -33,7 +33,8 @@ using SmemKernel = void (*)(const SmemParams);
 inline int smem_cta_threads(int method, int dc, int dv) { return (method == 1 && dc <= 8 && dv <= 4) ? 1024 : 512; }
 
 // defined in bp_smem_{ms,ps}.cu; nullptr when no degree bucket fits
-SmemKernel pick_smem_ms(int max_row_degree, int max_col_degree, bool llr);
-SmemKernel pick_smem_ps(int max_row_degree, int max_col_degree, bool llr);
+// `regular`: every row has exactly max_row_degree entries and every column exactly max_col_degree
+SmemKernel pick_smem_ms(int max_row_degree, int max_col_degree, bool regular, bool llr);
+SmemKernel pick_smem_ps(int max_row_degree, int max_col_degree, bool regular, bool llr);
 
 }  // namespace bpb

@@ -1,5 +1,7 @@
-// Instantiates the product-sum on-chip kernels (bp_smem.cuh); 512 threads per CTA (more registers per thread).
+// Instantiates the product-sum on-chip kernels (bp_smem.cuh) for every degree bucket.
 #include "bp_smem.cuh"
 namespace bpb {
-SmemKernel pick_smem_ps(int dc, int dv, bool llr) { return pick_smem_bucket<kProductSum>(dc, dv, llr); }
+SmemKernel pick_smem_ps(int dc, int dv, bool regular, bool llr) {
+    return pick_smem_bucket<kProductSum>(dc, dv, regular, llr);
+}
 }  // namespace bpb
