@@ -98,6 +98,9 @@ typedef struct {
     int64_t launches;         /* kernels launched by this handle so far */
     int64_t workspace_bytes;  /* device bytes held */
     double last_kernel_ms;    /* CUDA-event time of the last message-update kernel, 0 until it has finished */
+    int smem_family_available;    /* 1 when the on-chip kernel family can serve this code (parallel schedule) */
+    int smem_bank_multiplicity;   /* worst lanes-per-bank of a half-warp message access in that family (1 = none) */
+    int smem_bytes_per_syndrome;  /* shared memory held per in-flight syndrome in that family */
 } bpb_info;
 int bpb_get_info(const bpb_decoder *h, bpb_info *out);
 

@@ -30,7 +30,8 @@ class BpbInfo(C.Structure):
     _fields_ = [("m", C.c_int), ("n", C.c_int), ("nnz", C.c_int64), ("max_row_degree", C.c_int),
                 ("max_col_degree", C.c_int), ("device", C.c_int), ("sm_count", C.c_int), ("kernel_family", C.c_int),
                 ("grid", C.c_int), ("block", C.c_int), ("launches", C.c_int64), ("workspace_bytes", C.c_int64),
-                ("last_kernel_ms", C.c_double)]
+                ("last_kernel_ms", C.c_double), ("smem_family_available", C.c_int),
+                ("smem_bank_multiplicity", C.c_int), ("smem_bytes_per_syndrome", C.c_int)]
 
 
 EXPORTS = [

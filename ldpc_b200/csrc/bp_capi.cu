@@ -110,7 +110,7 @@ void build_smem_plan(bpb_decoder *h);
 
 // ---- graph blob ---------------------------------------------------------------------------------------
 
-int upload_graph(bpb_decoder *h) {
+void compute_priors(bpb_decoder *h) {
     const bpb::HostGraph &g = h->g;
     // priors on the host, the reference's expression (bp.hpp:150-151)
     h->prior.resize((size_t) g.n);
@@ -119,6 +119,11 @@ int upload_graph(bpb_decoder *h) {
         h->prior[(size_t) j] = std::log((1 - h->channel[(size_t) j]) / h->channel[(size_t) j]);
         if (std::memcmp(&h->prior[(size_t) j], &h->prior[0], sizeof(double)) != 0) h->uniform_prior = false;
     }
+}
+
+int upload_graph(bpb_decoder *h) {
+    const bpb::HostGraph &g = h->g;
+    compute_priors(h);
     size_t words = (size_t) (g.m + 1) + (size_t) g.nnz + (size_t) (g.n + 1) + (size_t) g.nnz + (size_t) g.nnz;
     if (words & 1) words++;
     h->prior_off = (uint32_t) words;
@@ -265,7 +270,7 @@ void build_smem_plan(bpb_decoder *h) {
         pl.why = "row degree > 32 or column degree > 16";
         return;
     }
-    if (DCm < 1 || (int64_t) DCm * M > 65535 || g.n > 65535) {
+    if (DCm < 1 || (int64_t) g.nnz + 16 * 17 > 65535 || g.n > 65535) {
         pl.why = "message positions do not fit 16-bit indices";
         return;
     }
@@ -280,6 +285,9 @@ void build_smem_plan(bpb_decoder *h) {
     pl.off_row_col = off;
     off += 2u * (uint32_t) (DCm * M);
     off = align_up(off, 4);
+    pl.off_row_pos = off;
+    off += 2u * (uint32_t) (DCm * M);
+    off = align_up(off, 4);
     pl.off_col_pos = off;
     off += 2u * (uint32_t) (DVm * N);
     off = align_up(off, 8);
@@ -290,15 +298,74 @@ void build_smem_plan(bpb_decoder *h) {
     uint8_t *row_deg = pl.blob.data() + pl.off_row_deg;
     uint8_t *col_deg = pl.blob.data() + pl.off_col_deg;
     uint16_t *row_col = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_row_col);
+    uint16_t *row_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_row_pos);
     uint16_t *col_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_pos);
+    // Message placement.  Every message is written by one thread and read by another: row threads touch it in the
+    // check pass (half-warp = 16 consecutive rows, same slot k), column threads in the bit pass (16 consecutive
+    // columns, same slot).  An 8-byte shared-memory access is served per half-warp and is conflict-free iff the 16
+    // lanes hit 16 different bank pairs.  Take the bipartite multigraph whose left nodes are the (row group, slot)
+    // cells, right nodes the (column group, slot) cells and whose edges are the nonzeros of H: every node has degree
+    // <= 16, so by Koenig's theorem its edges can be coloured with 16 colours such that no two edges at a node share
+    // a colour.  Colour = bank pair: both passes become conflict-free.  (Alternating-path edge colouring below.)
+    const int n_rc = ((g.m + 15) / 16) * DCm, n_cc = ((g.n + 15) / 16) * DVm;
+    std::vector<int> edge_rc((size_t) g.nnz), edge_cc((size_t) g.nnz), colour((size_t) g.nnz, -1);
+    std::vector<int> at_r((size_t) n_rc * 16, -1), at_c((size_t) n_cc * 16, -1);  // edge using colour q at the node
+    for (int i = 0; i < g.m; i++)
+        for (uint32_t q = g.row_ptr[(size_t) i]; q < g.row_ptr[(size_t) i + 1]; q++)
+            edge_rc[q] = (i / 16) * DCm + (int) (q - g.row_ptr[(size_t) i]);
+    for (int j = 0; j < g.n; j++)
+        for (uint32_t q = g.col_ptr[(size_t) j]; q < g.col_ptr[(size_t) j + 1]; q++)
+            edge_cc[g.csc2csr[q]] = (j / 16) * DVm + (int) (q - g.col_ptr[(size_t) j]);
+    for (int e = 0; e < g.nnz; e++) {
+        const int u = edge_rc[(size_t) e], v = edge_cc[(size_t) e];
+        int a = 0, b = 0;
+        while (at_r[(size_t) u * 16 + a] >= 0) a++;  // free at u (exists: degree <= 16 and e itself uncoloured)
+        while (at_c[(size_t) v * 16 + b] >= 0) b++;  // free at v
+        if (a != b) {
+            // walk the a/b alternating path that starts at v with colour a and swap a <-> b along it; it cannot
+            // reach u (bipartite, a is free at u), so afterwards a is free at both ends
+            std::vector<int> path;
+            int node = v, want = a;
+            bool on_col_side = true;
+            for (;;) {
+                const int f = on_col_side ? at_c[(size_t) node * 16 + want] : at_r[(size_t) node * 16 + want];
+                if (f < 0) break;
+                path.push_back(f);
+                node = on_col_side ? edge_rc[(size_t) f] : edge_cc[(size_t) f];
+                on_col_side = !on_col_side;
+                want = (want == a) ? b : a;
+            }
+            for (int f: path) {
+                at_r[(size_t) edge_rc[(size_t) f] * 16 + colour[(size_t) f]] = -1;
+                at_c[(size_t) edge_cc[(size_t) f] * 16 + colour[(size_t) f]] = -1;
+            }
+            for (int f: path) {
+                colour[(size_t) f] = (colour[(size_t) f] == a) ? b : a;
+                at_r[(size_t) edge_rc[(size_t) f] * 16 + colour[(size_t) f]] = f;
+                at_c[(size_t) edge_cc[(size_t) f] * 16 + colour[(size_t) f]] = f;
+            }
+        }
+        colour[(size_t) e] = a;
+        at_r[(size_t) u * 16 + a] = e;
+        at_c[(size_t) v * 16 + a] = e;
+    }
+    int per_colour[16] = {0};
     std::vector<uint32_t> slot_of_edge((size_t) g.nnz);
+    for (int e = 0; e < g.nnz; e++) slot_of_edge[(size_t) e] = (uint32_t) (colour[(size_t) e] + 16 * per_colour[colour[(size_t) e]]++);
+    int longest = 0;
+    for (int q = 0; q < 16; q++) longest = std::max(longest, per_colour[q]);
+    pl.msg_doubles = 16 * longest;
+    if (pl.msg_doubles > 65535) {
+        pl.why = "message positions do not fit 16-bit indices";
+        return;
+    }
     for (int i = 0; i < g.m; i++) {
         const uint32_t b = g.row_ptr[(size_t) i], e = g.row_ptr[(size_t) i + 1];
         row_deg[i] = (uint8_t) (e - b);
         for (uint32_t q = b; q < e; q++) {
             const uint32_t k = q - b;
             row_col[(size_t) k * M + i] = (uint16_t) g.col_idx[q];
-            slot_of_edge[q] = k * (uint32_t) M + (uint32_t) i;
+            row_pos[(size_t) k * M + i] = (uint16_t) slot_of_edge[q];
         }
     }
     for (int j = 0; j < g.n; j++) {
@@ -306,10 +373,23 @@ void build_smem_plan(bpb_decoder *h) {
         col_deg[j] = (uint8_t) (e - b);
         for (uint32_t q = b; q < e; q++) col_pos[(size_t) (q - b) * N + j] = (uint16_t) slot_of_edge[g.csc2csr[q]];
     }
+    // verify: largest number of lanes of one half-warp access that share a bank pair (1 = conflict-free)
+    pl.max_bank_multiplicity = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        const int items = pass == 0 ? g.m : g.n, stride = pass == 0 ? M : N, slots = pass == 0 ? DCm : DVm;
+        const uint16_t *tab = pass == 0 ? row_pos : col_pos;
+        const uint8_t *deg = pass == 0 ? row_deg : col_deg;
+        for (int base = 0; base < items; base += 16)
+            for (int k = 0; k < slots; k++) {
+                int cnt[16] = {0};
+                for (int x = base; x < std::min(items, base + 16); x++)
+                    if (k < deg[x]) pl.max_bank_multiplicity = std::max(pl.max_bank_multiplicity, ++cnt[tab[(size_t) k * stride + x] & 15]);
+            }
+    }
     if (!h->uniform_prior) std::memcpy(pl.blob.data() + pl.off_prior, h->prior.data(), 8 * (size_t) g.n);
     uint32_t go = 0;
     pl.goff_msg = go;
-    go += 8u * (uint32_t) (DCm * M);
+    go += 8u * (uint32_t) pl.msg_doubles;
     pl.goff_dec = go;
     go += (uint32_t) N / 8;  // one bit per column
     pl.goff_syn = go;
@@ -366,6 +446,7 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.off_row_deg = pl.off_row_deg;
     p.off_col_deg = pl.off_col_deg;
     p.off_row_col = pl.off_row_col;
+    p.off_row_pos = pl.off_row_pos;
     p.off_col_pos = pl.off_col_pos;
     p.off_prior = pl.off_prior;
     p.group_bytes = pl.group_bytes;
@@ -718,8 +799,16 @@ int bpb_osd0_host(bpb_decoder *h, const uint8_t *syndromes, const double *llr, c
     return rc;
 }
 
-int bpb_get_info(const bpb_decoder *h, bpb_info *out) {
+int bpb_get_info(const bpb_decoder *h_, bpb_info *out) {
+    bpb_decoder *h = const_cast<bpb_decoder *>(h_);
     if (!h || !out) return BPB_ERR_ARG;
+    if (h->device < 0 && !h->channel.empty() && h->graph_dirty) {
+        // host-only handle: the shared-memory plan is pure host work, build it so that it can be inspected
+        if (h->max_smem_optin <= 0) h->max_smem_optin = 232448;
+        compute_priors(h);
+        build_smem_plan(h);
+        h->graph_dirty = false;
+    }
     std::memset(out, 0, sizeof(*out));
     out->m = h->g.m;
     out->n = h->g.n;
@@ -733,8 +822,11 @@ int bpb_get_info(const bpb_decoder *h, bpb_info *out) {
     out->block = h->last_block;
     out->launches = h->launches;
     int64_t ws = 0;
-    for (bpb::DeviceBuffer *b: all_buffers(const_cast<bpb_decoder *>(h))) ws += (int64_t) b->bytes;
+    for (bpb::DeviceBuffer *b: all_buffers(h)) ws += (int64_t) b->bytes;
     out->workspace_bytes = ws;
+    out->smem_family_available = h->smem_plan.ok ? 1 : 0;
+    out->smem_bank_multiplicity = h->smem_plan.max_bank_multiplicity;
+    out->smem_bytes_per_syndrome = (int) h->smem_plan.group_bytes;
     if (h->kernel_timed) {
         // CUDA-event time of the most recent message-update kernel (valid once that launch has finished)
         float ms = 0;

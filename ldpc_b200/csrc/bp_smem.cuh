@@ -11,13 +11,15 @@
 // barrier.red.or for the convergence vote), so a group stuck on a 50-iteration non-converger does not hold up
 // its neighbours.
 //
-// Shared-memory layout of the messages: ELL by rows, msg[k*M + i] = message on the k-th edge (ascending column,
-// the reference's iterate_row order) of check i.  In the check pass thread i owns row i, so for fixed k the
-// lanes of a warp read consecutive doubles (conflict-free); as in the streaming family the update is in
-// place (b2c -> c2b -> b2c).  In the bit pass thread j owns column j and gathers its d_v messages through
-// col_pos[k*N + j] (the only accesses with bank conflicts).  Hard decisions are ballot words (one bit per column,
-// n <= 1024 bits sit in 32 different banks so the per-row gathers are conflict-free); the candidate syndrome
-// test (bp.hpp:292-300) is a per-row XOR over those bits followed by an OR-reduction barrier.
+// Shared-memory placement of the messages.  Thread i owns row i in the check pass, thread j owns column j in the
+// bit pass; the update is in place (b2c -> c2b -> b2c) like in the streaming family.  The position of every
+// message comes from two ELL tables, row_pos[k*M + i] (k-th edge of row i, ascending column = the reference's
+// iterate_row order) and col_pos[k*N + j] (k-th edge of column j, ascending row).  The host chooses the positions by
+// 16-colouring the edges of the (row half-warp, slot) x (column half-warp, slot) incidence graph (Koenig), colour
+// = shared-memory bank pair, so that both passes are free of bank conflicts (bp_capi.cu, build_smem_plan).
+// Hard decisions are ballot words (one bit per column, n <= 1024 bits sit in 32 different banks so the per-row
+// gathers are conflict-free too); the candidate syndrome test (bp.hpp:292-300) is a per-row XOR over those bits
+// followed by an OR-reduction barrier.
 #pragma once
 #include "bp_smem_params.h"
 #include "bp_update.cuh"
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
     const uint8_t *row_deg = sm + p.off_row_deg;
     const uint8_t *col_deg = sm + p.off_col_deg;
     const uint16_t *row_col = reinterpret_cast<const uint16_t *>(sm + p.off_row_col);
+    const uint16_t *row_pos = reinterpret_cast<const uint16_t *>(sm + p.off_row_pos);
     const uint16_t *col_pos = reinterpret_cast<const uint16_t *>(sm + p.off_col_pos);
     const double *prior = reinterpret_cast<const double *>(sm + p.off_prior);
     uint8_t *garea = sm + p.tab_bytes + (size_t) g * p.group_bytes;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
             syn[i] = (uint8_t) ((__ldg(srow + (i >> 5)) >> (i & 31)) & 1u);
             const int deg = UNI ? DC : row_deg[i];
             for (int k = 0; k < deg; ++k)
-                msg[k * M + i] = p.uniform_prior ? p.prior0 : prior[row_col[k * M + i]];
+                msg[row_pos[k * M + i]] = p.uniform_prior ? p.prior0 : prior[row_col[k * M + i]];
         }
         group_sync(bar, T);
 
@@ -87,13 +90,16 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
             // ---- check -> bit, one thread per row (bp.hpp:201-273) ----
             for (int i = t; i < m; i += T) {
                 const int deg = UNI ? DC : row_deg[i];
+                uint32_t rp[DC];
                 double b[DC], c[DC];
 #pragma unroll
-                for (int k = 0; k < DC; ++k) b[k] = (k < deg) ? msg[k * M + i] : 0.0;
+                for (int k = 0; k < DC; ++k) rp[k] = (k < deg) ? row_pos[k * M + i] : 0u;
+#pragma unroll
+                for (int k = 0; k < DC; ++k) b[k] = (k < deg) ? msg[rp[k]] : 0.0;
                 check_node_update<METHOD, DC>(b, deg, (uint32_t) syn[i], alpha, c);
 #pragma unroll
                 for (int k = 0; k < DC; ++k)
-                    if (k < deg) msg[k * M + i] = c[k];
+                    if (k < deg) msg[rp[k]] = c[k];
             }
             group_sync(bar, T);
             // ---- posterior, decision, bit -> check, one thread per column (bp.hpp:276-318) ----

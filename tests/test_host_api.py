@@ -227,3 +227,21 @@ def test_host_osd0_matches_oracle_and_reference(port_oracle, ref_oracle, threads
         lib.bpb_destroy(h)
         assert np.array_equal(out, dec)
         assert np.array_equal(out[~conv], port_oracle.osd0_batch(H, syn[~conv], llr[~conv]))
+
+
+@pytest.mark.parametrize("mk", [lambda: codes.regular_ldpc(1000, 3, 6, seed=1), codes.bivariate_bicycle_144,
+                                lambda: codes.rotated_surface_code_x(13), lambda: codes.hamming_code(5),
+                                lambda: codes.rep_code(40)], ids=["ldpc1000", "bb144", "surface13", "hamming5", "rep40"])
+def test_shared_memory_placement_is_conflict_free(mk):
+    """The on-chip family places messages by 16-colouring the (half-warp, slot) incidence graph (Koenig): no half-warp
+    of the check pass or of the bit pass may hit a bank pair twice."""
+    H = mk()
+    lib, h = _host_only_handle(H)
+    ch = np.full(H.shape[1], 0.05)
+    assert lib.bpb_set_channel(h, ch.ctypes.data_as(_capi._f64p), H.shape[1]) == 0
+    inf = _capi.BpbInfo()
+    assert lib.bpb_get_info(h, C.byref(inf)) == 0
+    lib.bpb_destroy(h)
+    assert inf.smem_family_available == 1
+    assert inf.smem_bank_multiplicity == 1
+    assert inf.smem_bytes_per_syndrome >= 8 * H.nnz
