@@ -101,6 +101,8 @@ typedef struct {
     int smem_family_available;    /* 1 when the on-chip kernel family can serve this code (parallel schedule) */
     int smem_bank_multiplicity;   /* worst lanes-per-bank of a half-warp message access in that family (1 = none) */
     int smem_bytes_per_syndrome;  /* shared memory held per in-flight syndrome in that family */
+    int64_t stream_iterations;    /* iterations executed by the last streaming-kernel launch (synchronises) */
+    int64_t stream_handed_off;    /* syndromes its ramp-down handed to the second-stage kernel */
 } bpb_info;
 int bpb_get_info(const bpb_decoder *h, bpb_info *out);
 

@@ -31,7 +31,8 @@ class BpbInfo(C.Structure):
                 ("max_col_degree", C.c_int), ("device", C.c_int), ("sm_count", C.c_int), ("kernel_family", C.c_int),
                 ("grid", C.c_int), ("block", C.c_int), ("launches", C.c_int64), ("workspace_bytes", C.c_int64),
                 ("last_kernel_ms", C.c_double), ("smem_family_available", C.c_int),
-                ("smem_bank_multiplicity", C.c_int), ("smem_bytes_per_syndrome", C.c_int)]
+                ("smem_bank_multiplicity", C.c_int), ("smem_bytes_per_syndrome", C.c_int),
+                ("stream_iterations", C.c_int64), ("stream_handed_off", C.c_int64)]
 
 
 EXPORTS = [

@@ -47,7 +47,7 @@ int ensure(bpb_decoder *h, bpb::DeviceBuffer &b, size_t bytes, bool zero = false
 
 std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
     return {&h->blob,     &h->order_d,   &h->counter,   &h->msg,        &h->dec_w,      &h->syn_w,    &h->llr_tile,
-            &h->packed,   &h->smem_tab,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
+            &h->packed,   &h->smem_tab,  &h->handoff,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
             &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1]};
 }
 
@@ -177,6 +177,10 @@ StreamKernel pick_stream(int method, int schedule, int dc, int dv, bool llr) {
     return nullptr;
 }
 
+int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
+                int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
+                const unsigned long long *batch_dev);
+
 int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
                   int32_t *d_iters, double *d_llr, cudaStream_t st) {
     const bpb::HostGraph &g = h->g;
@@ -215,8 +219,15 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     if ((rc = ensure(h, h->dec_w, warps * (size_t) n_pad * 4, true, st))) return rc;
     if ((rc = ensure(h, h->syn_w, p.smem_syn ? 16 : warps * (size_t) m_pad * 4, true, st))) return rc;
     if (llr && (rc = ensure(h, h->llr_tile, warps * (size_t) g.n * 32 * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->counter, 8))) return rc;
-    BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 8, st));
+    if ((rc = ensure(h, h->counter, 64))) return rc;
+    BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+    // second stage for the ramp-down (parallel schedule, when the thread-group kernels can take the code)
+    const bool second_stage = h->schedule == BPB_PARALLEL && h->smem_plan.ok && h->max_iter > 16;
+    if (second_stage && (rc = ensure(h, h->handoff, (size_t) warps * 32 * sizeof(uint32_t)))) return rc;
+    p.iter_cap = second_stage ? 12 : h->max_iter + 1;
+    p.handoff_count = (unsigned long long *) h->counter.ptr + 1;
+    p.handoff_list = (uint32_t *) h->handoff.ptr;
+    p.iter_total = (unsigned long long *) h->counter.ptr + 3;
 
     p.blob = (const uint32_t *) h->blob.ptr;
     p.blob_words = h->blob_words;
@@ -253,6 +264,14 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     h->last_family = BPB_KERNEL_STREAM;
     h->last_grid = grid;
     h->last_block = block;
+    if (second_stage) {
+        rc = launch_smem(h, d_packed, mwp, batch, d_dec, d_conv, d_iters, d_llr, st, (const uint32_t *) h->handoff.ptr,
+                         (const unsigned long long *) h->counter.ptr + 1);
+        if (rc) return rc;
+        h->last_family = BPB_KERNEL_STREAM;
+        h->last_grid = grid;
+        h->last_block = block;
+    }
     return BPB_OK;
 }
 
@@ -411,7 +430,8 @@ bpb::SmemKernel pick_smem(int method, int dc, int dv, bool regular, bool llr) {
 }
 
 int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
-                int32_t *d_iters, double *d_llr, cudaStream_t st) {
+                int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
+                const unsigned long long *batch_dev) {
     const bpb::HostGraph &g = h->g;
     const bpb::SmemPlan &pl = h->smem_plan;
     const bool llr = d_llr != nullptr;
@@ -438,8 +458,10 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     int64_t grid64 = std::min<int64_t>(h->sm_count, (batch + G - 1) / G);
     if (grid64 < 1) grid64 = 1;
     int rc;
-    if ((rc = ensure(h, h->counter, 8))) return rc;
-    BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 8, st));
+    if ((rc = ensure(h, h->counter, 64))) return rc;
+    // counter words: [0] streaming queue, [1] hand-off count, [2] thread-group queue
+    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+    if (index_list) grid64 = h->sm_count;  // the count lives on the device
     bpb::SmemParams p{};
     p.tab = (const uint32_t *) h->smem_tab.ptr;
     p.tab_bytes = (uint32_t) tab;
@@ -467,15 +489,17 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.synd_packed = d_packed;
     p.mwp = mwp;
     p.batch = batch;
-    p.counter = (unsigned long long *) h->counter.ptr;
+    p.counter = (unsigned long long *) h->counter.ptr + 2;
+    p.index_list = index_list;
+    p.batch_dev = batch_dev;
     p.out_dec = d_dec;
     p.out_conv = d_conv;
     p.out_iters = d_iters;
     p.out_llr = d_llr;
-    BPB_CUDA(h, cudaEventRecord(h->kev0, st));
+    if (!index_list) BPB_CUDA(h, cudaEventRecord(h->kev0, st));
     k<<<(int) grid64, block, smem_bytes, st>>>(p);
     BPB_CUDA(h, cudaGetLastError());
-    BPB_CUDA(h, cudaEventRecord(h->kev1, st));
+    if (!index_list) BPB_CUDA(h, cudaEventRecord(h->kev1, st));
     h->kernel_timed = true;
     h->launches += 1;
     h->last_family = BPB_KERNEL_SMEM;
@@ -714,7 +738,7 @@ int bpb_decode_batch_device(bpb_decoder *h, int input_type, const uint8_t *d_inp
         return BPB_ERR_UNSUPPORTED;
     }
     if (smem_able && h->kernel_pref != BPB_KERNEL_STREAM)
-        rc = launch_smem(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st);
+        rc = launch_smem(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st, nullptr, nullptr);
     else
         rc = launch_stream(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st);
     if (rc) return rc;
@@ -824,6 +848,13 @@ int bpb_get_info(const bpb_decoder *h_, bpb_info *out) {
     int64_t ws = 0;
     for (bpb::DeviceBuffer *b: all_buffers(h)) ws += (int64_t) b->bytes;
     out->workspace_bytes = ws;
+    if (h->device >= 0 && h->counter.ptr && h->last_family == BPB_KERNEL_STREAM) {
+        unsigned long long words[4] = {0, 0, 0, 0};
+        if (cudaMemcpy(words, h->counter.ptr, sizeof(words), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            out->stream_handed_off = (int64_t) words[1];
+            out->stream_iterations = (int64_t) words[3];
+        }
+    }
     out->smem_family_available = h->smem_plan.ok ? 1 : 0;
     out->smem_bank_multiplicity = h->smem_plan.max_bank_multiplicity;
     out->smem_bytes_per_syndrome = (int) h->smem_plan.group_bytes;

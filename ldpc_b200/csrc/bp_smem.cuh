@@ -67,11 +67,15 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
     uint8_t *syn = garea + p.goff_syn;
     volatile long long *ctl = reinterpret_cast<volatile long long *>(garea + p.goff_ctl);
 
+    const long long limit = p.batch_dev ? (long long) *p.batch_dev : p.batch;
     for (;;) {
-        if (t == 0) ctl[0] = (long long) atomicAdd(p.counter, 1ull);
+        if (t == 0) {
+            const long long claim = (long long) atomicAdd(p.counter, 1ull);
+            ctl[0] = (claim < limit) ? (p.index_list ? (long long) p.index_list[claim] : claim) : -1;
+        }
         group_sync(bar, T);
         const long long idx = ctl[0];
-        if (idx >= p.batch) break;
+        if (idx < 0) break;
         // syndrome bits and initialise_log_domain_bp (bp.hpp:147-157)
         const uint32_t *srow = p.synd_packed + idx * p.mwp;
         for (int i = t; i < m; i += T) {

@@ -20,6 +20,8 @@ struct SmemParams {
     int mwp;
     long long batch;
     unsigned long long *counter;
+    const uint32_t *index_list;             // second stage: batch indices to decode (null = 0..batch-1)
+    const unsigned long long *batch_dev;    // second stage: number of entries of index_list (device value)
     uint8_t *out_dec;     // [B][n]
     uint8_t *out_conv;    // [B] or null
     int32_t *out_iters;   // [B] or null

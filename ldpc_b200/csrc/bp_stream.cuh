@@ -346,6 +346,18 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
         const bool conv = active && !((mis >> lane) & 1u);
         const bool done = active && (conv || it >= p.max_iter);
         uint32_t donemask = __ballot_sync(0xffffffffu, done);
+        // Ramp-down: once the queue is empty, a lane that is still iterating after iter_cap iterations is a
+        // straggler that would keep its whole warp alive for up to maximum_iterations latency-bound sweeps.  Hand
+        // its syndrome to the second stage (decoded from scratch by the thread-group kernel; BP is deterministic,
+        // so the result is the same) instead of finishing it here.
+        const bool defer = active && !done && exhausted && it >= p.iter_cap;
+        const uint32_t defmask = __ballot_sync(0xffffffffu, defer);
+        if (defmask) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(p.handoff_count, (unsigned long long) __popc(defmask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (defer) p.handoff_list[base + __popc(defmask & lanemask_lt())] = (uint32_t) idx;
+        }
 
         // ---------------- retire finished syndromes ------------------------------------------------
         while (donemask) {
@@ -375,7 +387,10 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
                 for (int j = lane; j < n; j += 32) dst[j] = __ldcg(src + (size_t) j * 32);
             }
         }
-        if (done) idx = -1;
+        if (done || defer) {
+            atomicAdd(p.iter_total, (unsigned long long) it);  // iterations this kernel really executed (roofline)
+            idx = -1;
+        }
     }
 }
 

@@ -29,6 +29,10 @@ struct StreamParams {
     double *out_llr;      // [B][n] or null
     const uint32_t *order;  // serial schedule order (device), order_len entries
     int order_len;
+    int iter_cap;                       // hand-off threshold (>= max_iter disables the second stage)
+    unsigned long long *handoff_count;  // number of syndromes handed to the second stage
+    uint32_t *handoff_list;             // their batch indices
+    unsigned long long *iter_total;     // sum of iterations executed by this launch
     int smem_graph, smem_syn;
     uint32_t smem_syn_off;  // word offset of the per-warp syndrome words in dynamic shared memory
 };
