@@ -107,6 +107,7 @@ __global__ void xor_received_kernel(uint8_t *__restrict__ dec, const uint8_t *__
 }
 
 void build_smem_plan(bpb_decoder *h);
+std::vector<uint32_t> build_serial_batches(const bpb::HostGraph &g, const std::vector<uint32_t> &order, int sb);
 
 // ---- graph blob ---------------------------------------------------------------------------------------
 
@@ -149,9 +150,11 @@ int upload_graph(bpb_decoder *h) {
         h->serial_order.resize((size_t) g.n);
         for (int j = 0; j < g.n; j++) h->serial_order[(size_t) j] = (uint32_t) j;
     }
-    rc = ensure(h, h->order_d, h->serial_order.size() * sizeof(uint32_t));
+    h->serial_batches = build_serial_batches(g, h->serial_order,
+                                             bpb::serial_batch(g.max_row_degree, g.max_col_degree, g.regular));
+    rc = ensure(h, h->order_d, h->serial_batches.size() * sizeof(uint32_t));
     if (rc) return rc;
-    BPB_CUDA(h, cudaMemcpyAsync(h->order_d.ptr, h->serial_order.data(), h->serial_order.size() * sizeof(uint32_t),
+    BPB_CUDA(h, cudaMemcpyAsync(h->order_d.ptr, h->serial_batches.data(), h->serial_batches.size() * sizeof(uint32_t),
                                 cudaMemcpyHostToDevice, h->stream));
     build_smem_plan(h);
     if (h->smem_plan.ok) {
@@ -169,12 +172,37 @@ int upload_graph(bpb_decoder *h) {
 
 using bpb::StreamKernel;
 
-StreamKernel pick_stream(int method, int schedule, int dc, int dv, bool llr) {
-    if (method == BPB_MINIMUM_SUM && schedule == BPB_PARALLEL) return bpb::pick_stream_ms_parallel(dc, dv, llr);
-    if (method == BPB_PRODUCT_SUM && schedule == BPB_PARALLEL) return bpb::pick_stream_ps_parallel(dc, dv, llr);
-    if (method == BPB_MINIMUM_SUM && schedule == BPB_SERIAL) return bpb::pick_stream_ms_serial(dc, dv, llr);
-    if (method == BPB_PRODUCT_SUM && schedule == BPB_SERIAL) return bpb::pick_stream_ps_serial(dc, dv, llr);
+StreamKernel pick_stream(int method, int schedule, int dc, int dv, bool reg, bool llr) {
+    if (method == BPB_MINIMUM_SUM && schedule == BPB_PARALLEL) return bpb::pick_stream_ms_parallel(dc, dv, reg, llr);
+    if (method == BPB_PRODUCT_SUM && schedule == BPB_PARALLEL) return bpb::pick_stream_ps_parallel(dc, dv, reg, llr);
+    if (method == BPB_MINIMUM_SUM && schedule == BPB_SERIAL) return bpb::pick_stream_ms_serial(dc, dv, reg, llr);
+    if (method == BPB_PRODUCT_SUM && schedule == BPB_SERIAL) return bpb::pick_stream_ps_serial(dc, dv, reg, llr);
     return nullptr;
+}
+
+// Levelise the serial schedule (see the serial branch of bp_stream.cuh): level(q) = 1 + max level of the earlier
+// schedule positions whose bit shares a check with this one; stable-sort by level; cut each level into batches of
+// `sb` bits, padding the last batch of a level with 0xffffffff.
+std::vector<uint32_t> build_serial_batches(const bpb::HostGraph &g, const std::vector<uint32_t> &order, int sb) {
+    std::vector<int> last_level((size_t) g.m, 0), level(order.size(), 0);
+    int max_level = 0;
+    for (size_t q = 0; q < order.size(); q++) {
+        const uint32_t j = order[q];
+        int lv = 0;
+        for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) lv = std::max(lv, last_level[g.row_idx[e]]);
+        lv += 1;
+        for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) last_level[g.row_idx[e]] = lv;
+        level[q] = lv;
+        max_level = std::max(max_level, lv);
+    }
+    std::vector<std::vector<uint32_t>> by_level((size_t) max_level + 1);
+    for (size_t q = 0; q < order.size(); q++) by_level[(size_t) level[q]].push_back(order[q]);
+    std::vector<uint32_t> out;
+    for (const auto &bits: by_level) {
+        for (uint32_t j: bits) out.push_back(j);
+        while (out.size() % (size_t) sb) out.push_back(0xffffffffu);
+    }
+    return out;
 }
 
 int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
@@ -185,7 +213,7 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
                   int32_t *d_iters, double *d_llr, cudaStream_t st) {
     const bpb::HostGraph &g = h->g;
     const bool llr = d_llr != nullptr;
-    StreamKernel k = pick_stream(h->method, h->schedule, g.max_row_degree, g.max_col_degree, llr);
+    StreamKernel k = pick_stream(h->method, h->schedule, g.max_row_degree, g.max_col_degree, g.regular, llr);
     if (!k) {
         h->err = "stream kernels support row degree <= 32 and column degree <= 16 (got " +
                  std::to_string(g.max_row_degree) + ", " + std::to_string(g.max_col_degree) + ")";
@@ -254,7 +282,7 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     p.out_iters = d_iters;
     p.out_llr = d_llr;
     p.order = (const uint32_t *) h->order_d.ptr;
-    p.order_len = (int) h->serial_order.size();
+    p.order_len = (int) h->serial_batches.size();
     BPB_CUDA(h, cudaEventRecord(h->kev0, st));
     k<<<grid, block, smem_bytes, st>>>(p);
     BPB_CUDA(h, cudaGetLastError());

@@ -20,15 +20,18 @@
 // syndrome; syn_w[i] likewise for the syndrome.  The candidate-syndrome test of bp.hpp:292-300 then
 // costs one XOR per (row, column) pair per warp instead of per syndrome.
 #pragma once
-#include "bp_common.cuh"
 #include "bp_stream_params.h"
+#include "bp_update.cuh"
 
 namespace bpb {
 
-template <int DC> struct RowsPerBatch { static constexpr int v = DC <= 8 ? 2 : 1; };
-template <int DV> struct ColsPerBatch { static constexpr int v = DV <= 4 ? 4 : 1; };
+// How many rows / columns / serial-schedule bits a lane keeps in flight per step (loads are issued for the whole
+// batch before any of it is consumed: memory-level parallelism per warp = batch * degree 256-byte transactions).
+template <int DC, bool UNI> struct RowsPerBatch { static constexpr int v = UNI ? 4 : (DC <= 8 ? 2 : 1); };
+template <int DV, bool UNI> struct ColsPerBatch { static constexpr int v = UNI ? 8 : (DV <= 4 ? 4 : 1); };
 
-template <int METHOD, int SCHED, int DC, int DV, bool LLR>
+// UNI: every row has exactly DC entries and every column exactly DV (regular codes): no degree predication.
+template <int METHOD, int SCHED, int DC, int DV, bool LLR, bool UNI>
 __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
 
         if (SCHED == kParallel) {
             // ---------------- check -> bit (bp.hpp:201-273), in place --------------------------------
-            constexpr int RB = RowsPerBatch<DC>::v;
+            constexpr int RB = RowsPerBatch<DC, UNI>::v;
             for (int i0 = 0; i0 < m; i0 += RB) {
                 uint32_t beg[RB];
                 int deg[RB];
@@ -122,7 +125,10 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     const int i = i0 + r;
-                    if (i < m) {
+                    if (UNI) {
+                        beg[r] = (uint32_t) (i < m ? i : 0) * DC;
+                        deg[r] = (i < m) ? DC : 0;
+                    } else if (i < m) {
                         beg[r] = row_ptr[i];
                         deg[r] = (int) (row_ptr[i + 1] - beg[r]);
                     } else {
@@ -148,63 +154,14 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
                     if (i >= m) continue;
                     const uint32_t s = (syn_w[i] >> lane) & 1u;
                     double c[DC];
-                    if (METHOD == kMinimumSum) {
-                        // bp.hpp:231-271: total sign, min over the other edges, scaled
-                        uint32_t tsgn = s;
-                        double min1 = DBL_MAX, min2 = DBL_MAX;
-                        int arg = -1;
-#pragma unroll
-                        for (int k = 0; k < DC; ++k) {
-                            if (k < deg[r]) {
-                                if (b[r][k] <= 0) tsgn += 1;
-                                const double a = fabs(b[r][k]);
-                                if (a < min1) {
-                                    min2 = min1;
-                                    min1 = a;
-                                    arg = k;
-                                } else if (a < min2) {
-                                    min2 = a;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < DC; ++k) {
-                            if (k < deg[r]) {
-                                const double mag = (k == arg) ? min2 : min1;
-                                const uint32_t sg = tsgn + ((b[r][k] <= 0) ? 1u : 0u);
-                                c[k] = mag * ((sg & 1u) ? -alpha : alpha);
-                            }
-                        }
-                    } else {
-                        // bp.hpp:202-218: prefix products forward, suffix products backward
-                        double t[DC];
-                        double pre = 1.0;
-#pragma unroll
-                        for (int k = 0; k < DC; ++k) {
-                            if (k < deg[r]) {
-                                t[k] = ps_tanh_half(b[r][k]);
-                                c[k] = pre;
-                                pre *= t[k];
-                            }
-                        }
-                        double suf = 1.0;
-                        const double sigma = s ? -1.0 : 1.0;
-#pragma unroll
-                        for (int k = DC - 1; k >= 0; --k) {
-                            if (k < deg[r]) {
-                                const double x = c[k] * suf;
-                                c[k] = sigma * ps_atanh2(x);
-                                suf *= t[k];
-                            }
-                        }
-                    }
+                    check_node_update<METHOD, DC>(b[r], UNI ? DC : deg[r], s, alpha, c);
 #pragma unroll
                     for (int k = 0; k < DC; ++k)
                         if (active && k < deg[r]) st_msg(tile + (size_t) (beg[r] + k) * 32, c[k]);
                 }
             }
             // ---------------- bit pass: posterior, decision, b2c (bp.hpp:276-318), in place ----------
-            constexpr int CB = ColsPerBatch<DV>::v;
+            constexpr int CB = ColsPerBatch<DV, UNI>::v;
             uint32_t acc_w = 0;
             for (int j0 = 0; j0 < n; j0 += CB) {
                 uint32_t eid[CB][DV];
@@ -216,8 +173,8 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
                     uint32_t beg = 0;
                     deg[r] = 0;
                     if (j < n) {
-                        beg = col_ptr[j];
-                        deg[r] = (int) (col_ptr[j + 1] - beg);
+                        beg = UNI ? (uint32_t) j * DV : col_ptr[j];
+                        deg[r] = UNI ? DV : (int) (col_ptr[j + 1] - beg);
                     }
 #pragma unroll
                     for (int k = 0; k < DV; ++k) eid[r][k] = (k < deg[r]) ? csc2csr[beg + k] : 0u;
@@ -235,15 +192,7 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
                 for (int r = 0; r < CB; ++r) {
                     const int j = j0 + r;
                     if (j >= n) continue;
-                    double pre[DV];
-                    double t = p.uniform_prior ? p.prior0 : prior[j];
-#pragma unroll
-                    for (int k = 0; k < DV; ++k) {
-                        if (k < deg[r]) {
-                            pre[k] = t;
-                            t += c[r][k];
-                        }
-                    }
+                    const double t = bit_node_update<DV>(c[r], UNI ? DV : deg[r], p.uniform_prior ? p.prior0 : prior[j]);
                     const bool x = (t <= 0);
                     if (LLR) {
                         if (active) llr_tile[(size_t) j * 32] = t;
@@ -251,84 +200,100 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
                     const uint32_t W = __ballot_sync(0xffffffffu, active && x);
                     if (lane == (j & 31)) acc_w = W;
                     if ((j & 31) == 31 || j == n - 1) dec_w[(j & ~31) + lane] = acc_w;
-                    double u = 0;
 #pragma unroll
-                    for (int k = DV - 1; k >= 0; --k) {
-                        if (k < deg[r]) {
-                            const double bn = pre[k] + u;
-                            u += c[r][k];
-                            if (active) st_msg(tile + (size_t) eid[r][k] * 32, bn);
-                        }
-                    }
+                    for (int k = 0; k < DV; ++k)
+                        if (active && k < deg[r]) st_msg(tile + (size_t) eid[r][k] * 32, c[r][k]);
                 }
             }
         } else {
             // ---------------- serial schedule (bp.hpp:484-534) ----------------------------------------
-            for (int oi = 0; oi < p.order_len; ++oi) {  // one bit at a time, in schedule order
-                const int j = (int) p.order[oi];
-                const uint32_t cbeg = col_ptr[j];
-                const int cdeg = (int) (col_ptr[j + 1] - cbeg);
-                double L = p.uniform_prior ? p.prior0 : prior[j];
-                double c[DV], pre[DV];
-                uint32_t eid[DV];
+            // The reference updates the bits one after another.  Two bits that share no check touch disjoint
+            // messages (bit j reads the b2c of the OTHER edges of its checks and writes its own edges), so they
+            // commute; the host sorts the schedule into levels (level(j) > level of every earlier bit that shares a
+            // check with j, bp_capi.cu: build_serial_batches) and hands the kernel batches of SB bits of one level.
+            // All loads of a batch are issued before any of its stores, which multiplies the transactions in
+            // flight per warp by SB; the result is the reference's, bit for bit.
+            constexpr int SB = SerialBatch<DC, DV, UNI>::v;
+            for (int o0 = 0; o0 < p.order_len; o0 += SB) {
+                uint32_t jj[SB], eid[SB][DV], rbeg[SB][DV];
+                int cdeg[SB], rdeg[SB][DV];
+                double bv[SB][DV][DC];
 #pragma unroll
-                for (int k = 0; k < DV; ++k) {
-                    if (k < cdeg) {
-                        const uint32_t e = csc2csr[cbeg + k];
-                        const uint32_t i = row_idx[cbeg + k];
-                        const uint32_t rbeg = row_ptr[i];
-                        const int rdeg = (int) (row_ptr[i + 1] - rbeg);
-                        const uint32_t s = (syn_w[i] >> lane) & 1u;
-                        eid[k] = e;
-                        double bv[DC];
+                for (int q = 0; q < SB; ++q) {
+                    jj[q] = p.order[o0 + q];
+                    const bool valid = jj[q] != 0xffffffffu;
+                    const uint32_t j = valid ? jj[q] : 0u;
+                    const uint32_t cbeg = UNI ? j * DV : col_ptr[j];
+                    cdeg[q] = valid ? (UNI ? DV : (int) (col_ptr[j + 1] - cbeg)) : 0;
+#pragma unroll
+                    for (int k = 0; k < DV; ++k) {
+                        eid[q][k] = 0;
+                        rbeg[q][k] = 0;
+                        rdeg[q][k] = 0;
+                        if (k < cdeg[q]) {
+                            eid[q][k] = csc2csr[cbeg + k];
+                            const uint32_t i = row_idx[cbeg + k];
+                            rbeg[q][k] = UNI ? i * DC : row_ptr[i];
+                            rdeg[q][k] = UNI ? DC : (int) (row_ptr[i + 1] - rbeg[q][k]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < SB; ++q)
+#pragma unroll
+                    for (int k = 0; k < DV; ++k)
 #pragma unroll
                         for (int f = 0; f < DC; ++f) {
                             double v = 0.0;
-                            if (active && f < rdeg && rbeg + f != e) v = ld_msg(tile + (size_t) (rbeg + f) * 32);
-                            bv[f] = v;
+                            if (active && f < rdeg[q][k] && rbeg[q][k] + f != eid[q][k])
+                                v = ld_msg(tile + (size_t) (rbeg[q][k] + f) * 32);
+                            bv[q][k][f] = v;
                         }
-                        if (METHOD == kMinimumSum) {
-                            uint32_t sg = s;
-                            double temp = DBL_MAX;
 #pragma unroll
-                            for (int f = 0; f < DC; ++f) {
-                                if (f < rdeg && rbeg + f != e) {
-                                    const double a = fabs(bv[f]);
-                                    if (a < temp) temp = a;
-                                    if (bv[f] <= 0) sg += 1;
+                for (int q = 0; q < SB; ++q) {
+                    if (jj[q] == 0xffffffffu) continue;  // padding at the end of a level (warp-uniform)
+                    const uint32_t j = jj[q];
+                    const uint32_t cbeg = UNI ? j * DV : col_ptr[j];
+                    double c[DV];
+#pragma unroll
+                    for (int k = 0; k < DV; ++k) {
+                        if (k < cdeg[q]) {
+                            const uint32_t i = row_idx[cbeg + k];
+                            const uint32_t s = (syn_w[i] >> lane) & 1u;
+                            if (METHOD == kMinimumSum) {
+                                // bp.hpp:503-519
+                                uint32_t sg = s;
+                                double temp = DBL_MAX;
+#pragma unroll
+                                for (int f = 0; f < DC; ++f) {
+                                    if (f < rdeg[q][k] && rbeg[q][k] + f != eid[q][k]) {
+                                        const double a = fabs(bv[q][k][f]);
+                                        if (a < temp) temp = a;
+                                        if (bv[q][k][f] <= 0) sg += 1;
+                                    }
                                 }
-                            }
-                            c[k] = ((sg & 1u) ? -alpha : alpha) * temp;
-                        } else {
-                            double x = 1.0;
+                                c[k] = ((sg & 1u) ? -alpha : alpha) * temp;
+                            } else {
+                                // bp.hpp:489-498
+                                double x = 1.0;
 #pragma unroll
-                            for (int f = 0; f < DC; ++f)
-                                if (f < rdeg && rbeg + f != e) x *= ps_tanh_half(bv[f]);
-                            c[k] = (s ? -1.0 : 1.0) * ps_atanh2(x);
+                                for (int f = 0; f < DC; ++f)
+                                    if (f < rdeg[q][k] && rbeg[q][k] + f != eid[q][k]) x *= ps_tanh_half(bv[q][k][f]);
+                                c[k] = (s ? -1.0 : 1.0) * ps_atanh2(x);
+                            }
                         }
                     }
-                }
-#pragma unroll
-                for (int k = 0; k < DV; ++k) {
-                    if (k < cdeg) {
-                        pre[k] = L;
-                        L += c[k];
+                    // bp.hpp:499-500 / 520-533: b2c := running sum, posterior, decision, extrinsic b2c
+                    const double L = bit_node_update<DV>(c, cdeg[q], p.uniform_prior ? p.prior0 : prior[j]);
+                    const bool x = (L <= 0);
+                    if (LLR) {
+                        if (active) llr_tile[(size_t) j * 32] = L;
                     }
-                }
-                const bool x = (L <= 0);
-                if (LLR) {
-                    if (active) llr_tile[(size_t) j * 32] = L;
-                }
-                const uint32_t W = __ballot_sync(0xffffffffu, active && x);
-                if (lane == 0) dec_w[j] = W;
-                double u = 0;
+                    const uint32_t W = __ballot_sync(0xffffffffu, active && x);
+                    if (lane == 0) dec_w[j] = W;
 #pragma unroll
-                for (int k = DV - 1; k >= 0; --k) {
-                    if (k < cdeg) {
-                        const double bn = pre[k] + u;
-                        u += c[k];
-                        if (active) st_msg(tile + (size_t) eid[k] * 32, bn);
-                    }
+                    for (int k = 0; k < DV; ++k)
+                        if (active && k < cdeg[q]) st_msg(tile + (size_t) eid[q][k] * 32, c[k]);
                 }
             }
         }
@@ -396,13 +361,15 @@ __global__ void __launch_bounds__(256) bp_stream_kernel(const StreamParams p) {
 
 // One translation unit per (method, schedule) instantiates its degree buckets through this helper.
 template <int METHOD, int SCHED>
-StreamKernel pick_stream_bucket(int dc, int dv, bool llr) {
-#define BPB_PICK(DC_, DV_) \
-    return llr ? bp_stream_kernel<METHOD, SCHED, DC_, DV_, true> : bp_stream_kernel<METHOD, SCHED, DC_, DV_, false>
-    if (dc <= 8 && dv <= 4) { BPB_PICK(8, 4); }
-    if (dc <= 8 && dv <= 16) { BPB_PICK(8, 16); }
-    if (dc <= 32 && dv <= 4) { BPB_PICK(32, 4); }
-    if (dc <= 32 && dv <= 16) { BPB_PICK(32, 16); }
+StreamKernel pick_stream_bucket(int dc, int dv, bool regular, bool llr) {
+#define BPB_PICK(DC_, DV_, UNI_)                                                   \
+    return llr ? bp_stream_kernel<METHOD, SCHED, DC_, DV_, true, UNI_>             \
+               : bp_stream_kernel<METHOD, SCHED, DC_, DV_, false, UNI_>
+    if (regular && dc == 6 && dv == 3) { BPB_PICK(6, 3, true); }  // (3,6)-regular LDPC, bivariate bicycle
+    if (dc <= 8 && dv <= 4) { BPB_PICK(8, 4, false); }
+    if (dc <= 8 && dv <= 16) { BPB_PICK(8, 16, false); }
+    if (dc <= 32 && dv <= 4) { BPB_PICK(32, 4, false); }
+    if (dc <= 32 && dv <= 16) { BPB_PICK(32, 16, false); }
 #undef BPB_PICK
     return nullptr;
 }

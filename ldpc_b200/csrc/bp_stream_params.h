@@ -27,7 +27,7 @@ struct StreamParams {
     uint8_t *out_conv;    // [B] or null
     int32_t *out_iters;   // [B] or null
     double *out_llr;      // [B][n] or null
-    const uint32_t *order;  // serial schedule order (device), order_len entries
+    const uint32_t *order;  // serial schedule: levelised batches of SerialBatch bits, 0xffffffff = padding
     int order_len;
     int iter_cap;                       // hand-off threshold (>= max_iter disables the second stage)
     unsigned long long *handoff_count;  // number of syndromes handed to the second stage
@@ -39,10 +39,18 @@ struct StreamParams {
 
 using StreamKernel = void (*)(const StreamParams);
 
+// Bits of one level the serial-schedule kernel keeps in flight together (host pads the schedule to this).
+template <int DC, int DV, bool UNI> struct SerialBatch { static constexpr int v = UNI ? 4 : ((DC <= 8 && DV <= 4) ? 2 : 1); };
+inline int serial_batch(int dc, int dv, bool regular) {
+    if (regular && dc == 6 && dv == 3) return SerialBatch<6, 3, true>::v;
+    if (dc <= 8 && dv <= 4) return SerialBatch<8, 4, false>::v;
+    return 1;
+}
+
 // defined in bp_stream_{ms,ps}_{parallel,serial}.cu; nullptr when no degree bucket fits
-StreamKernel pick_stream_ms_parallel(int max_row_degree, int max_col_degree, bool llr);
-StreamKernel pick_stream_ps_parallel(int max_row_degree, int max_col_degree, bool llr);
-StreamKernel pick_stream_ms_serial(int max_row_degree, int max_col_degree, bool llr);
-StreamKernel pick_stream_ps_serial(int max_row_degree, int max_col_degree, bool llr);
+StreamKernel pick_stream_ms_parallel(int max_row_degree, int max_col_degree, bool regular, bool llr);
+StreamKernel pick_stream_ps_parallel(int max_row_degree, int max_col_degree, bool regular, bool llr);
+StreamKernel pick_stream_ms_serial(int max_row_degree, int max_col_degree, bool regular, bool llr);
+StreamKernel pick_stream_ps_serial(int max_row_degree, int max_col_degree, bool regular, bool llr);
 
 }  // namespace bpb
