@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbp_b200.so")
+LIB_PATH = os.environ.get("LDPC_B200_LIB") or os.path.join(_HERE, "libbp_b200.so")  # env var: experimental builds
 
 _u8p = C.POINTER(C.c_uint8)
 _i32p = C.POINTER(C.c_int32)
@@ -38,7 +38,7 @@ class BpbInfo(C.Structure):
 EXPORTS = [
     "bpb_create", "bpb_destroy", "bpb_last_error", "bpb_set_channel", "bpb_set_max_iter", "bpb_set_method",
     "bpb_set_schedule", "bpb_set_ms_scaling_factor", "bpb_set_serial_schedule_order", "bpb_set_kernel",
-    "bpb_decode_batch", "bpb_decode_batch_device", "bpb_osd0_host", "bpb_get_info", "bpb_host_alloc",
+    "bpb_decode_batch", "bpb_decode_batch_device", "bpb_osd0_host", "bpb_bposd_decode_batch", "bpb_get_info", "bpb_host_alloc",
     "bpb_host_free", "bpb_version",
 ]
 
@@ -77,6 +77,8 @@ def lib():
     L.bpb_decode_batch_device.argtypes = [vp, C.c_int, vp, C.c_int64, vp, vp, vp, vp, vp]
     L.bpb_osd0_host.restype = C.c_int
     L.bpb_osd0_host.argtypes = [vp, vp, vp, vp, C.c_int64, vp, C.c_int]
+    L.bpb_bposd_decode_batch.restype = C.c_int
+    L.bpb_bposd_decode_batch.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int]
     L.bpb_get_info.restype = C.c_int
     L.bpb_get_info.argtypes = [vp, C.POINTER(BpbInfo)]
     L.bpb_host_alloc.restype = vp
@@ -100,6 +102,49 @@ def check(handle, rc: int) -> None:
 
 def host_ptr(a: np.ndarray | None):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class _PinnedBlock:
+    """Owner of one pinned allocation; goes back to the pool when the numpy arrays built on it are gone."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    def __del__(self):
+        try:
+            _pool_give(self.ptr, self.nbytes)
+        except Exception:
+            pass
+
+
+_POOL = {}            # nbytes -> [ptr, ...] free pinned blocks
+_POOL_BYTES = [0]     # bytes currently allocated through the pool (free + in use)
+_POOL_LIMIT = int(os.environ.get("LDPC_B200_PINNED_LIMIT", str(8 << 30)))
+
+
+def _pool_give(ptr, nbytes):
+    _POOL.setdefault(nbytes, []).append(ptr)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (full-speed, asynchronous PCIe copies), recycled through a small pool.
+    Falls back to ordinary memory when the pool limit is reached or pinning fails."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = max(64, (count * dtype.itemsize + 4095) // 4096 * 4096)
+    free = _POOL.get(nbytes)
+    if free:
+        ptr = free.pop()
+    else:
+        if _POOL_BYTES[0] + nbytes > _POOL_LIMIT:
+            return np.empty(shape, dtype=dtype)
+        ptr = lib().bpb_host_alloc(nbytes)
+        if not ptr:
+            return np.empty(shape, dtype=dtype)
+        _POOL_BYTES[0] += nbytes
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    buf._owner = _PinnedBlock(ptr, nbytes)  # keeps the block out of the pool while any view of `buf` lives
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
 class PinnedArray:

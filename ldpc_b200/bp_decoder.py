@@ -144,10 +144,12 @@ class BpDecoderBase:
         """inputs: contiguous uint8 [B, m|n].  Returns (decoding u8 [B,n], converged bool[B], iters i32[B], llr|None)."""
         h = self._ensure_handle()
         B = inputs.shape[0]
-        dec = np.empty((B, self.n), dtype=np.uint8)
-        conv = np.empty(B, dtype=np.uint8)
-        its = np.empty(B, dtype=np.int32)
-        llr = np.empty((B, self.n), dtype=np.float64) if want_llr else None
+        big = B * self.n >= (1 << 20)  # large results land in pinned memory (asynchronous D2H at full PCIe speed)
+        alloc = _capi.pinned_empty if big else np.empty
+        dec = alloc((B, self.n), dtype=np.uint8)
+        conv = alloc((B,), dtype=np.uint8)
+        its = alloc((B,), dtype=np.int32)
+        llr = alloc((B, self.n), dtype=np.float64) if want_llr else None
         rc = _capi.lib().bpb_decode_batch(h, input_type, _capi.host_ptr(inputs), B, _capi.host_ptr(dec),
                                           _capi.host_ptr(conv), _capi.host_ptr(its), _capi.host_ptr(llr))
         _capi.check(h, rc)

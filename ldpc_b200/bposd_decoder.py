@@ -117,11 +117,21 @@ class BpOsdDecoder(BpDecoderBase):
         vec = np.ascontiguousarray(arr.astype(np.uint8, copy=False))
         if vec.shape[0] == 0:
             return np.zeros((0, self.n), dtype=dtype)
-        dec, conv, its, llr = self._decode_device_batch(vec, _capi.INPUT_SYNDROME, want_llr=True)
-        self.converge_batch, self.iter_batch, self.log_prob_ratios_batch = conv, its, llr
-        self.bp_decoding_batch = dec.copy() if not conv.all() else dec
-        if not conv.all():
-            self._osd0(vec, llr, conv, dec)
+        if self._osd_method != OSD_OFF and self._osd_order != 0:
+            raise NotImplementedError("only OSD-0 (osd_order == 0) is implemented; OSD_E / OSD_CS are out of scope")
+        h = self._ensure_handle()
+        B = vec.shape[0]
+        dec = np.empty((B, self.n), dtype=np.uint8)
+        conv = np.empty(B, dtype=np.uint8)
+        its = np.empty(B, dtype=np.int32)
+        if self._osd_method == OSD_OFF:
+            d, c, i, _ = self._decode_device_batch(vec, _capi.INPUT_SYNDROME, want_llr=False)
+            dec, conv, its = d, c.astype(np.uint8), i
+        else:
+            rc = _capi.lib().bpb_bposd_decode_batch(h, _capi.host_ptr(vec), B, _capi.host_ptr(dec), _capi.host_ptr(conv),
+                                                    _capi.host_ptr(its), None, self._osd_threads)
+            _capi.check(h, rc)
+        self.converge_batch, self.iter_batch, self.log_prob_ratios_batch = conv.astype(bool), its, None
         return dec if dtype == np.uint8 else dec.astype(dtype)
 
     @property

@@ -47,7 +47,7 @@ int ensure(bpb_decoder *h, bpb::DeviceBuffer &b, size_t bytes, bool zero = false
 
 std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
     return {&h->blob,     &h->order_d,   &h->counter,   &h->msg,        &h->dec_w,      &h->syn_w,    &h->llr_tile,
-            &h->packed,   &h->smem_tab,  &h->handoff,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
+            &h->packed,   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
             &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1]};
 }
 
@@ -108,6 +108,24 @@ __global__ void xor_received_kernel(uint8_t *__restrict__ dec, const uint8_t *__
 
 void build_smem_plan(bpb_decoder *h);
 std::vector<uint32_t> build_serial_batches(const bpb::HostGraph &g, const std::vector<uint32_t> &order, int sb);
+
+// BP+OSD: gather the posterior LLR rows of the syndromes BP did not solve (one warp per syndrome) so that only
+// those cross PCIe (the reference hands bpd.log_prob_ratios to OSD only when !bpd.converge, _bposd_decoder.pyx:128-134)
+__global__ void compact_failures_kernel(const uint8_t *__restrict__ conv, const double *__restrict__ llr,
+                                        long long batch, int n, unsigned long long *count,
+                                        uint32_t *__restrict__ fail_idx, double *__restrict__ fail_llr) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+    for (long long b = warp; b < batch; b += nwarps) {
+        if (conv[b]) continue;
+        unsigned long long slot = 0;
+        if (lane == 0) slot = atomicAdd(count, 1ull);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (lane == 0) fail_idx[slot] = (uint32_t) b;
+        for (int j = lane; j < n; j += 32) fail_llr[slot * n + j] = llr[b * n + j];
+    }
+}
 
 // ---- graph blob ---------------------------------------------------------------------------------------
 
@@ -329,14 +347,14 @@ void build_smem_plan(bpb_decoder *h) {
     pl.off_col_deg = off;
     off += (uint32_t) N;
     off = align_up(off, 4);
+    // 16-bit entries, two slots (2q, 2q+1) of the same row / column packed into one 32-bit word: tab[q*stride + x]
+    const int DCp = (DCm + 1) / 2, DVp = (DVm + 1) / 2;
     pl.off_row_col = off;
-    off += 2u * (uint32_t) (DCm * M);
-    off = align_up(off, 4);
+    off += 4u * (uint32_t) (DCp * M);
     pl.off_row_pos = off;
-    off += 2u * (uint32_t) (DCm * M);
-    off = align_up(off, 4);
+    off += 4u * (uint32_t) (DCp * M);
     pl.off_col_pos = off;
-    off += 2u * (uint32_t) (DVm * N);
+    off += 4u * (uint32_t) (DVp * N);
     off = align_up(off, 8);
     pl.off_prior = off;
     if (!h->uniform_prior) off += 8u * (uint32_t) g.n;
@@ -411,14 +429,15 @@ void build_smem_plan(bpb_decoder *h) {
         row_deg[i] = (uint8_t) (e - b);
         for (uint32_t q = b; q < e; q++) {
             const uint32_t k = q - b;
-            row_col[(size_t) k * M + i] = (uint16_t) g.col_idx[q];
-            row_pos[(size_t) k * M + i] = (uint16_t) slot_of_edge[q];
+            row_col[2 * ((size_t) (k / 2) * M + i) + (k & 1)] = (uint16_t) g.col_idx[q];
+            row_pos[2 * ((size_t) (k / 2) * M + i) + (k & 1)] = (uint16_t) slot_of_edge[q];
         }
     }
     for (int j = 0; j < g.n; j++) {
         const uint32_t b = g.col_ptr[(size_t) j], e = g.col_ptr[(size_t) j + 1];
         col_deg[j] = (uint8_t) (e - b);
-        for (uint32_t q = b; q < e; q++) col_pos[(size_t) (q - b) * N + j] = (uint16_t) slot_of_edge[g.csc2csr[q]];
+        for (uint32_t q = b; q < e; q++)
+            col_pos[2 * ((size_t) ((q - b) / 2) * N + j) + ((q - b) & 1)] = (uint16_t) slot_of_edge[g.csc2csr[q]];
     }
     // verify: largest number of lanes of one half-warp access that share a bank pair (1 = conflict-free)
     pl.max_bank_multiplicity = 0;
@@ -430,7 +449,9 @@ void build_smem_plan(bpb_decoder *h) {
             for (int k = 0; k < slots; k++) {
                 int cnt[16] = {0};
                 for (int x = base; x < std::min(items, base + 16); x++)
-                    if (k < deg[x]) pl.max_bank_multiplicity = std::max(pl.max_bank_multiplicity, ++cnt[tab[(size_t) k * stride + x] & 15]);
+                    if (k < deg[x])
+                        pl.max_bank_multiplicity = std::max(
+                            pl.max_bank_multiplicity, ++cnt[tab[2 * ((size_t) (k / 2) * stride + x) + (k & 1)] & 15]);
             }
     }
     if (!h->uniform_prior) std::memcpy(pl.blob.data() + pl.off_prior, h->prior.data(), 8 * (size_t) g.n);
@@ -849,6 +870,77 @@ int bpb_osd0_host(bpb_decoder *h, const uint8_t *syndromes, const double *llr, c
     int rc = bpb::osd0_host(h->g, syndromes, llr, converged, batch, decoding, threads);
     if (rc) h->err = "osd0_host failed";
     return rc;
+}
+
+int bpb_bposd_decode_batch(bpb_decoder *h, const uint8_t *syndromes, int64_t batch, uint8_t *decoding,
+                           uint8_t *converged, int32_t *iterations, uint8_t *bp_decoding, int threads) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (batch < 0 || (batch > 0 && (!syndromes || !decoding))) {
+        h->err = "bad decode arguments";
+        return BPB_ERR_ARG;
+    }
+    if (batch == 0) return BPB_OK;
+    BPB_CUDA(h, cudaSetDevice(h->device));
+    if (h->graph_dirty && (rc = upload_graph(h))) return rc;
+    const bpb::HostGraph &g = h->g;
+    const int64_t chunk_max = (int64_t) 1 << 17;
+    const size_t cap = (size_t) std::min(chunk_max, batch);
+    if ((rc = ensure(h, h->osd_llr, cap * g.n * 8))) return rc;
+    if ((rc = ensure(h, h->osd_fail_llr, cap * g.n * 8))) return rc;
+    if ((rc = ensure(h, h->osd_fail_idx, cap * 4))) return rc;
+    if ((rc = ensure(h, h->osd_count, 16))) return rc;
+    std::vector<uint8_t> host_conv(cap);
+    std::vector<uint32_t> fidx;
+    std::vector<double> fllr;
+    std::vector<uint8_t> fsyn, fdec;
+    for (int64_t lo = 0; lo < batch; lo += chunk_max) {
+        const int64_t nb = std::min(chunk_max, batch - lo);
+        if ((rc = ensure(h, h->st_in[0], cap * g.m))) return rc;
+        if ((rc = ensure(h, h->st_dec[0], cap * g.n))) return rc;
+        if ((rc = ensure(h, h->st_conv[0], cap))) return rc;
+        if ((rc = ensure(h, h->st_iters[0], cap * 4))) return rc;
+        cudaStream_t st = h->stream;
+        BPB_CUDA(h, cudaMemcpyAsync(h->st_in[0].ptr, syndromes + lo * g.m, (size_t) nb * g.m, cudaMemcpyHostToDevice, st));
+        rc = bpb_decode_batch_device(h, BPB_INPUT_SYNDROME, (const uint8_t *) h->st_in[0].ptr, nb,
+                                     (uint8_t *) h->st_dec[0].ptr, (uint8_t *) h->st_conv[0].ptr,
+                                     (int32_t *) h->st_iters[0].ptr, (double *) h->osd_llr.ptr, st);
+        if (rc) return rc;
+        BPB_CUDA(h, cudaMemsetAsync(h->osd_count.ptr, 0, 16, st));
+        const int cgrid = (int) std::min<int64_t>((nb + 7) / 8, (int64_t) h->sm_count * 16);
+        compact_failures_kernel<<<cgrid, 256, 0, st>>>((const uint8_t *) h->st_conv[0].ptr, (const double *) h->osd_llr.ptr,
+                                                      nb, g.n, (unsigned long long *) h->osd_count.ptr,
+                                                      (uint32_t *) h->osd_fail_idx.ptr, (double *) h->osd_fail_llr.ptr);
+        BPB_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+        unsigned long long nfail = 0;
+        BPB_CUDA(h, cudaMemcpyAsync(decoding + lo * g.n, h->st_dec[0].ptr, (size_t) nb * g.n, cudaMemcpyDeviceToHost, st));
+        BPB_CUDA(h, cudaMemcpyAsync(host_conv.data(), h->st_conv[0].ptr, (size_t) nb, cudaMemcpyDeviceToHost, st));
+        if (iterations)
+            BPB_CUDA(h, cudaMemcpyAsync(iterations + lo, h->st_iters[0].ptr, (size_t) nb * 4, cudaMemcpyDeviceToHost, st));
+        BPB_CUDA(h, cudaMemcpyAsync(&nfail, h->osd_count.ptr, 8, cudaMemcpyDeviceToHost, st));
+        BPB_CUDA(h, cudaStreamSynchronize(st));
+        if (converged) std::memcpy(converged + lo, host_conv.data(), (size_t) nb);
+        if (bp_decoding) std::memcpy(bp_decoding + lo * g.n, decoding + lo * g.n, (size_t) nb * g.n);
+        if (nfail) {
+            fidx.resize(nfail);
+            fllr.resize(nfail * (size_t) g.n);
+            fsyn.resize(nfail * (size_t) g.m);
+            fdec.assign(nfail * (size_t) g.n, 0);
+            BPB_CUDA(h, cudaMemcpy(fidx.data(), h->osd_fail_idx.ptr, nfail * 4, cudaMemcpyDeviceToHost));
+            BPB_CUDA(h, cudaMemcpy(fllr.data(), h->osd_fail_llr.ptr, nfail * (size_t) g.n * 8, cudaMemcpyDeviceToHost));
+            for (size_t q = 0; q < nfail; q++)
+                std::memcpy(&fsyn[q * g.m], syndromes + (lo + fidx[q]) * g.m, (size_t) g.m);
+            rc = bpb::osd0_host(g, fsyn.data(), fllr.data(), nullptr, (int64_t) nfail, fdec.data(), threads);
+            if (rc) {
+                h->err = "osd0_host failed";
+                return rc;
+            }
+            for (size_t q = 0; q < nfail; q++)
+                std::memcpy(decoding + (lo + fidx[q]) * g.n, &fdec[q * g.n], (size_t) g.n);
+        }
+    }
+    return BPB_OK;
 }
 
 int bpb_get_info(const bpb_decoder *h_, bpb_info *out) {

@@ -65,6 +65,7 @@ struct bpb_decoder {
     // device state
     bool graph_dirty = true;  // blob must be (re)uploaded (prior or order changed)
     bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed, smem_tab, handoff;
+    bpb::DeviceBuffer osd_llr, osd_fail_llr, osd_fail_idx, osd_count;  // BP+OSD batch path
     bpb::SmemPlan smem_plan;
     // staging for the host API
     bpb::DeviceBuffer st_in[2], st_dec[2], st_conv[2], st_iters[2], st_llr[2];

@@ -26,6 +26,11 @@
 
 namespace bpb {
 
+// entry `k` of row / column x in a pair-packed 16-bit table
+__device__ __forceinline__ uint32_t slot16(const uint32_t *tab, int stride, int x, int k) {
+    return (tab[(k >> 1) * stride + x] >> ((k & 1) * 16)) & 0xffffu;
+}
+
 __device__ __forceinline__ void group_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -57,9 +62,10 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
     const int m = p.m, n = p.n, M = p.M, N = p.N;
     const uint8_t *row_deg = sm + p.off_row_deg;
     const uint8_t *col_deg = sm + p.off_col_deg;
-    const uint16_t *row_col = reinterpret_cast<const uint16_t *>(sm + p.off_row_col);
-    const uint16_t *row_pos = reinterpret_cast<const uint16_t *>(sm + p.off_row_pos);
-    const uint16_t *col_pos = reinterpret_cast<const uint16_t *>(sm + p.off_col_pos);
+    // 16-bit tables, slots (2q, 2q+1) of one row / column packed in the 32-bit word tab[q*stride + x]
+    const uint32_t *row_col = reinterpret_cast<const uint32_t *>(sm + p.off_row_col);
+    const uint32_t *row_pos = reinterpret_cast<const uint32_t *>(sm + p.off_row_pos);
+    const uint32_t *col_pos = reinterpret_cast<const uint32_t *>(sm + p.off_col_pos);
     const double *prior = reinterpret_cast<const double *>(sm + p.off_prior);
     uint8_t *garea = sm + p.tab_bytes + (size_t) g * p.group_bytes;
     double *msg = reinterpret_cast<double *>(garea + p.goff_msg);
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
             syn[i] = (uint8_t) ((__ldg(srow + (i >> 5)) >> (i & 31)) & 1u);
             const int deg = UNI ? DC : row_deg[i];
             for (int k = 0; k < deg; ++k)
-                msg[row_pos[k * M + i]] = p.uniform_prior ? p.prior0 : prior[row_col[k * M + i]];
+                msg[slot16(row_pos, M, i, k)] = p.uniform_prior ? p.prior0 : prior[slot16(row_col, M, i, k)];
         }
         group_sync(bar, T);
 
@@ -97,7 +103,11 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
                 uint32_t rp[DC];
                 double b[DC], c[DC];
 #pragma unroll
-                for (int k = 0; k < DC; ++k) rp[k] = (k < deg) ? row_pos[k * M + i] : 0u;
+                for (int q = 0; q < (DC + 1) / 2; ++q) {
+                    const uint32_t w = (2 * q < deg) ? row_pos[q * M + i] : 0u;
+                    rp[2 * q] = w & 0xffffu;
+                    if (2 * q + 1 < DC) rp[2 * q + 1] = w >> 16;
+                }
 #pragma unroll
                 for (int k = 0; k < DC; ++k) b[k] = (k < deg) ? msg[rp[k]] : 0.0;
                 check_node_update<METHOD, DC>(b, deg, (uint32_t) syn[i], alpha, c);
@@ -115,7 +125,11 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
                     uint32_t pos[DV];
                     double c[DV];
 #pragma unroll
-                    for (int k = 0; k < DV; ++k) pos[k] = (k < deg) ? col_pos[k * N + j] : 0u;
+                    for (int q = 0; q < (DV + 1) / 2; ++q) {
+                        const uint32_t w = (2 * q < deg) ? col_pos[q * N + j] : 0u;
+                        pos[2 * q] = w & 0xffffu;
+                        if (2 * q + 1 < DV) pos[2 * q + 1] = w >> 16;
+                    }
 #pragma unroll
                     for (int k = 0; k < DV; ++k) c[k] = (k < deg) ? msg[pos[k]] : 0.0;
                     const double llr = bit_node_update<DV>(c, deg, p.uniform_prior ? p.prior0 : prior[j]);
@@ -135,17 +149,14 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
             uint32_t bad = 0;
             for (int i = t; i < m; i += T) {
                 uint32_t par = syn[i];
-                if (UNI) {
+                const int deg = UNI ? DC : row_deg[i];
 #pragma unroll
-                    for (int k = 0; k < DC; ++k) {
-                        const uint32_t cj = row_col[k * M + i];
-                        par ^= dec[cj >> 5] >> (cj & 31);
-                    }
-                } else {
-                    const int deg = row_deg[i];
-                    for (int k = 0; k < deg; ++k) {
-                        const uint32_t cj = row_col[k * M + i];
-                        par ^= dec[cj >> 5] >> (cj & 31);
+                for (int q = 0; q < (DC + 1) / 2; ++q) {
+                    if (2 * q < deg) {
+                        const uint32_t w = row_col[q * M + i];
+                        const uint32_t c0 = w & 0xffffu, c1 = w >> 16;
+                        par ^= dec[c0 >> 5] >> (c0 & 31);
+                        if (2 * q + 1 < deg) par ^= dec[c1 >> 5] >> (c1 & 31);
                     }
                 }
                 bad |= par & 1u;

@@ -40,7 +40,10 @@ struct StreamParams {
 using StreamKernel = void (*)(const StreamParams);
 
 // Bits of one level the serial-schedule kernel keeps in flight together (host pads the schedule to this).
-template <int DC, int DV, bool UNI> struct SerialBatch { static constexpr int v = UNI ? 4 : ((DC <= 8 && DV <= 4) ? 2 : 1); };
+#ifndef BPB_SERIAL_SB_UNI
+#define BPB_SERIAL_SB_UNI 4
+#endif
+template <int DC, int DV, bool UNI> struct SerialBatch { static constexpr int v = UNI ? BPB_SERIAL_SB_UNI : ((DC <= 8 && DV <= 4) ? 2 : 1); };
 inline int serial_batch(int dc, int dv, bool regular) {
     if (regular && dc == 6 && dv == 3) return SerialBatch<6, 3, true>::v;
     if (dc <= 8 && dv <= 4) return SerialBatch<8, 4, false>::v;
