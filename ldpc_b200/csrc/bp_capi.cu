@@ -168,12 +168,26 @@ int upload_graph(bpb_decoder *h) {
         h->serial_order.resize((size_t) g.n);
         for (int j = 0; j < g.n; j++) h->serial_order[(size_t) j] = (uint32_t) j;
     }
-    h->serial_batches = build_serial_batches(g, h->serial_order,
-                                             bpb::serial_batch(g.max_row_degree, g.max_col_degree, g.regular));
-    rc = ensure(h, h->order_d, h->serial_batches.size() * sizeof(uint32_t));
+    const int sb = bpb::serial_batch(g.max_row_degree, g.max_col_degree, g.regular);
+    h->serial_batches = build_serial_batches(g, h->serial_order, sb);
+    std::vector<uint32_t> upload = h->serial_batches;
+    h->serial_entries = (int) h->serial_batches.size();
+    if (g.regular && g.max_row_degree == 6 && g.max_col_degree == 3 && g.m < (1 << 28)) {
+        // regular-code serial program (see bp_stream.cuh): {j, row | self << 28 for each of the three edges}
+        upload.assign(h->serial_batches.size() * 4, 0xffffffffu);
+        for (size_t q = 0; q < h->serial_batches.size(); q++) {
+            const uint32_t j = h->serial_batches[q];
+            if (j == 0xffffffffu) continue;
+            upload[4 * q] = j;
+            for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) {
+                const uint32_t i = g.row_idx[e], self = g.csc2csr[e] - g.row_ptr[i];
+                upload[4 * q + 1 + (e - g.col_ptr[j])] = i | (self << 28);
+            }
+        }
+    }
+    rc = ensure(h, h->order_d, upload.size() * sizeof(uint32_t));
     if (rc) return rc;
-    BPB_CUDA(h, cudaMemcpyAsync(h->order_d.ptr, h->serial_batches.data(), h->serial_batches.size() * sizeof(uint32_t),
-                                cudaMemcpyHostToDevice, h->stream));
+    BPB_CUDA(h, cudaMemcpy(h->order_d.ptr, upload.data(), upload.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     build_smem_plan(h);
     if (h->smem_plan.ok) {
         rc = ensure(h, h->smem_tab, h->smem_plan.blob.size());
@@ -300,7 +314,7 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     p.out_iters = d_iters;
     p.out_llr = d_llr;
     p.order = (const uint32_t *) h->order_d.ptr;
-    p.order_len = (int) h->serial_batches.size();
+    p.order_len = h->serial_entries;
     BPB_CUDA(h, cudaEventRecord(h->kev0, st));
     k<<<grid, block, smem_bytes, st>>>(p);
     BPB_CUDA(h, cudaGetLastError());

@@ -61,6 +61,7 @@ struct bpb_decoder {
     double ms_scaling = 0.625;
     std::vector<uint32_t> serial_order;
     std::vector<uint32_t> serial_batches;  // levelised, padded schedule the serial kernels consume
+    int serial_entries = 0;                // number of schedule entries (bits + padding)
     int kernel_pref = BPB_KERNEL_AUTO;
     // device state
     bool graph_dirty = true;  // blob must be (re)uploaded (prior or order changed)

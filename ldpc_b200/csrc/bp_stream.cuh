@@ -216,6 +216,75 @@ __global__ void __launch_bounds__(256, (SCHED == kParallel && DC <= 8 && DV <= 4
             // All loads of a batch are issued before any of its stores, which multiplies the transactions in
             // flight per warp by SB; the result is the reference's, bit for bit.
             constexpr int SB = SerialBatch<DC, DV, UNI>::v;
+            if (UNI) {
+                // Regular codes: the host compiles the levelised schedule into a program of one 128-bit word per
+                // (bit, padding included): {j, w_0, w_1, w_2,...}, w_k = row index | self position << 28, so the
+                // only dependent step between the (sequential, warp-uniform) program fetch and the message loads
+                // is address arithmetic.  Of a row's DC contiguous messages the DC-1 that are not the bit's own
+                // are loaded: offset f + (f >= self).
+                static_assert(!UNI || DV <= 3, "program word layout holds three edges");
+                const uint4 *prog = reinterpret_cast<const uint4 *>(p.order);
+                for (int o0 = 0; o0 < p.order_len; o0 += SB) {
+                    uint4 pw[SB];
+                    double bv[SB][DV][DC - 1];
+#pragma unroll
+                    for (int q = 0; q < SB; ++q) pw[q] = __ldg(prog + o0 + q);
+#pragma unroll
+                    for (int q = 0; q < SB; ++q) {
+                        const uint32_t wk[3] = {pw[q].y, pw[q].z, pw[q].w};
+#pragma unroll
+                        for (int k = 0; k < DV; ++k) {
+                            const uint32_t rb = (wk[k] & 0x0fffffffu) * DC, sp = wk[k] >> 28;
+#pragma unroll
+                            for (int f = 0; f < DC - 1; ++f) {
+                                double v = 0.0;
+                                if (active && pw[q].x != 0xffffffffu)
+                                    v = ld_msg(tile + (size_t) (rb + f + (f >= (int) sp ? 1 : 0)) * 32);
+                                bv[q][k][f] = v;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < SB; ++q) {
+                        if (pw[q].x == 0xffffffffu) continue;  // padding at the end of a level (warp-uniform)
+                        const uint32_t j = pw[q].x;
+                        const uint32_t wk[3] = {pw[q].y, pw[q].z, pw[q].w};
+                        double c[DV];
+#pragma unroll
+                        for (int k = 0; k < DV; ++k) {
+                            const uint32_t i = wk[k] & 0x0fffffffu;
+                            const uint32_t s = (syn_w[i] >> lane) & 1u;
+                            if (METHOD == kMinimumSum) {
+                                uint32_t sg = s;  // bp.hpp:503-519
+                                double temp = DBL_MAX;
+#pragma unroll
+                                for (int f = 0; f < DC - 1; ++f) {
+                                    const double a = fabs(bv[q][k][f]);
+                                    if (a < temp) temp = a;
+                                    if (bv[q][k][f] <= 0) sg += 1;
+                                }
+                                c[k] = ((sg & 1u) ? -alpha : alpha) * temp;
+                            } else {
+                                double x = 1.0;  // bp.hpp:489-498
+#pragma unroll
+                                for (int f = 0; f < DC - 1; ++f) x *= ps_tanh_half(bv[q][k][f]);
+                                c[k] = (s ? -1.0 : 1.0) * ps_atanh2(x);
+                            }
+                        }
+                        const double L = bit_node_update<DV>(c, DV, p.uniform_prior ? p.prior0 : prior[j]);
+                        if (LLR) {
+                            if (active) llr_tile[(size_t) j * 32] = L;
+                        }
+                        const uint32_t W = __ballot_sync(0xffffffffu, active && (L <= 0));
+                        if (lane == 0) dec_w[j] = W;
+#pragma unroll
+                        for (int k = 0; k < DV; ++k) {
+                            const uint32_t e = (wk[k] & 0x0fffffffu) * DC + (wk[k] >> 28);
+                            if (active) st_msg(tile + (size_t) e * 32, c[k]);
+                        }
+                    }
+                }
+            } else
             for (int o0 = 0; o0 < p.order_len; o0 += SB) {
                 uint32_t jj[SB], eid[SB][DV], rbeg[SB][DV];
                 int cdeg[SB], rdeg[SB][DV];
