@@ -98,6 +98,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def load_traffic():
+    """DRAM bytes per launch of the message-update kernels from the committed ncu captures (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def host_cores():
     """CPU threads this process may actually use: min(affinity, cgroup cpu.max quota)."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -264,15 +273,9 @@ def run_ours(args, rank, local_rank, world):
                 if info["kernel_family"] == 2 else "streaming family: messages resident in HBM",
                 "mean_iterations": its_sum / B, "converged_fraction": conv_frac,
                 "handed_to_second_stage": int(info["stream_handed_off"]) if info["kernel_family"] == 1 else 0}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
-    if os.path.exists(traffic_file):
-        try:
-            with open(traffic_file) as f:
-                tr = json.load(f)
-            if tr.get("batch") == B and tr.get("kernel") == roofline["kernel"]:
-                roofline["traffic"] = tr["dram_bytes_per_launch"]
-        except Exception:
-            pass
+    traffic = load_traffic()
+    if roofline["kernel"] in traffic and traffic[roofline["kernel"]].get("batch") == B:
+        roofline["traffic"] = traffic[roofline["kernel"]]["dram_bytes_per_launch"]  # ncu --set full, per launch
 
     # ---- the streaming (HBM-resident) family on the same batch, for the record ----------------------------------
     stream_family = None
@@ -304,7 +307,9 @@ def run_ours(args, rank, local_rank, world):
                          "roofline": {"bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s",
                                       "frac": s_ach / peak, "kernel": "bp_stream_kernel",
                                       "kernel_ms": sinfo["last_kernel_ms"], "algorithmic_bytes_per_launch": s_bytes,
-                                      "handed_to_second_stage": int(sinfo["stream_handed_off"])},
+                                      "handed_to_second_stage": int(sinfo["stream_handed_off"]),
+                                      "traffic": (traffic.get("bp_stream_kernel", {}).get("dram_bytes_per_launch")
+                                                  if traffic.get("bp_stream_kernel", {}).get("batch") == B else None)},
                          "note": "same batch decoded by the HBM-streaming kernel family (kernel='stream'): messages "
                                  "laid out batch-minor in HBM, one lane per syndrome"}
         del sdec

@@ -349,7 +349,7 @@ void build_smem_plan(bpb_decoder *h) {
         pl.why = "row degree > 32 or column degree > 16";
         return;
     }
-    if (DCm < 1 || (int64_t) g.nnz + 16 * 17 > 65535 || g.n > 65535) {
+    if (DCm < 1 || (int64_t) g.nnz + 16 * 17 > 65535 || g.n > 65535 || g.m > 65535) {
         pl.why = "message positions do not fit 16-bit indices";
         return;
     }
@@ -363,8 +363,8 @@ void build_smem_plan(bpb_decoder *h) {
     off = align_up(off, 4);
     // 16-bit entries, two slots (2q, 2q+1) of the same row / column packed into one 32-bit word: tab[q*stride + x]
     const int DCp = (DCm + 1) / 2, DVp = (DVm + 1) / 2;
-    pl.off_row_col = off;
-    off += 4u * (uint32_t) (DCp * M);
+    pl.off_col_row = off;
+    off += 4u * (uint32_t) (DVp * N);
     pl.off_row_pos = off;
     off += 4u * (uint32_t) (DCp * M);
     pl.off_col_pos = off;
@@ -376,7 +376,7 @@ void build_smem_plan(bpb_decoder *h) {
     pl.blob.assign(off, 0);
     uint8_t *row_deg = pl.blob.data() + pl.off_row_deg;
     uint8_t *col_deg = pl.blob.data() + pl.off_col_deg;
-    uint16_t *row_col = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_row_col);
+    uint16_t *col_row = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_row);
     uint16_t *row_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_row_pos);
     uint16_t *col_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_pos);
     // Message placement.  Every message is written by one thread and read by another: row threads touch it in the
@@ -443,15 +443,16 @@ void build_smem_plan(bpb_decoder *h) {
         row_deg[i] = (uint8_t) (e - b);
         for (uint32_t q = b; q < e; q++) {
             const uint32_t k = q - b;
-            row_col[2 * ((size_t) (k / 2) * M + i) + (k & 1)] = (uint16_t) g.col_idx[q];
             row_pos[2 * ((size_t) (k / 2) * M + i) + (k & 1)] = (uint16_t) slot_of_edge[q];
         }
     }
     for (int j = 0; j < g.n; j++) {
         const uint32_t b = g.col_ptr[(size_t) j], e = g.col_ptr[(size_t) j + 1];
         col_deg[j] = (uint8_t) (e - b);
-        for (uint32_t q = b; q < e; q++)
+        for (uint32_t q = b; q < e; q++) {
             col_pos[2 * ((size_t) ((q - b) / 2) * N + j) + ((q - b) & 1)] = (uint16_t) slot_of_edge[g.csc2csr[q]];
+            col_row[2 * ((size_t) ((q - b) / 2) * N + j) + ((q - b) & 1)] = (uint16_t) g.row_idx[q];
+        }
     }
     // verify: largest number of lanes of one half-warp access that share a bank pair (1 = conflict-free)
     pl.max_bank_multiplicity = 0;
@@ -475,7 +476,7 @@ void build_smem_plan(bpb_decoder *h) {
     pl.goff_dec = go;
     go += (uint32_t) N / 8;  // one bit per column
     pl.goff_syn = go;
-    go += (uint32_t) M;
+    go += 2u * 4u * (uint32_t) ((g.m + 31) / 32);  // packed syndrome + candidate accumulator
     go = align_up(go, 8);
     pl.goff_ctl = go;
     go += 8;
@@ -530,7 +531,7 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.tab_bytes = (uint32_t) tab;
     p.off_row_deg = pl.off_row_deg;
     p.off_col_deg = pl.off_col_deg;
-    p.off_row_col = pl.off_row_col;
+    p.off_col_row = pl.off_col_row;
     p.off_row_pos = pl.off_row_pos;
     p.off_col_pos = pl.off_col_pos;
     p.off_prior = pl.off_prior;
@@ -543,6 +544,7 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.n = g.n;
     p.M = pl.M;
     p.N = pl.N;
+    p.MW = (g.m + 31) / 32;
     p.groups = G;
     p.T = T;
     p.max_iter = h->max_iter;

@@ -37,7 +37,7 @@ struct SmemPlan {
     bool ok = false;
     std::string why;            // why the family is not usable for this code (when !ok)
     std::vector<uint8_t> blob;  // tables in their final shared-memory byte layout
-    uint32_t off_row_deg = 0, off_col_deg = 0, off_row_col = 0, off_row_pos = 0, off_col_pos = 0, off_prior = 0;
+    uint32_t off_row_deg = 0, off_col_deg = 0, off_col_row = 0, off_row_pos = 0, off_col_pos = 0, off_prior = 0;
     int max_bank_multiplicity = 0;  // 1 = both passes conflict-free (verified by build_smem_plan)
     int msg_doubles = 0;        // length of one group's message array (16 * largest colour class)
     uint32_t group_bytes = 0, goff_msg = 0, goff_dec = 0, goff_syn = 0, goff_ctl = 0;

@@ -17,9 +17,9 @@
 // iterate_row order) and col_pos[k*N + j] (k-th edge of column j, ascending row).  The host chooses the positions by
 // 16-colouring the edges of the (row half-warp, slot) x (column half-warp, slot) incidence graph (Koenig), colour
 // = shared-memory bank pair, so that both passes are free of bank conflicts (bp_capi.cu, build_smem_plan).
-// Hard decisions are ballot words (one bit per column, n <= 1024 bits sit in 32 different banks so the per-row
-// gathers are conflict-free too); the candidate syndrome test (bp.hpp:292-300) is a per-row XOR over those bits
-// followed by an OR-reduction barrier.
+// Hard decisions are ballot words (one bit per column).  The candidate syndrome (bp.hpp:290-300) is accumulated the
+// way the reference does it, from the columns: a bit decided 1 XORs its checks into a word array preset to the
+// syndrome (shared-memory atomicXor; only ~p*n bits are 1), and an OR-reduction barrier tests it for zero.
 #pragma once
 #include "bp_smem_params.h"
 #include "bp_update.cuh"
@@ -63,14 +63,15 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
     const uint8_t *row_deg = sm + p.off_row_deg;
     const uint8_t *col_deg = sm + p.off_col_deg;
     // 16-bit tables, slots (2q, 2q+1) of one row / column packed in the 32-bit word tab[q*stride + x]
-    const uint32_t *row_col = reinterpret_cast<const uint32_t *>(sm + p.off_row_col);
+    const uint32_t *col_row = reinterpret_cast<const uint32_t *>(sm + p.off_col_row);
     const uint32_t *row_pos = reinterpret_cast<const uint32_t *>(sm + p.off_row_pos);
     const uint32_t *col_pos = reinterpret_cast<const uint32_t *>(sm + p.off_col_pos);
     const double *prior = reinterpret_cast<const double *>(sm + p.off_prior);
     uint8_t *garea = sm + p.tab_bytes + (size_t) g * p.group_bytes;
     double *msg = reinterpret_cast<double *>(garea + p.goff_msg);
     uint32_t *dec = reinterpret_cast<uint32_t *>(garea + p.goff_dec);  // hard decisions, one bit per column
-    uint8_t *syn = garea + p.goff_syn;
+    uint32_t *synw = reinterpret_cast<uint32_t *>(garea + p.goff_syn);  // packed syndrome, then the candidate
+    uint32_t *acc = synw + p.MW;                                        // syndrome accumulator (XOR)
     volatile long long *ctl = reinterpret_cast<volatile long long *>(garea + p.goff_ctl);
 
     const long long limit = p.batch_dev ? (long long) *p.batch_dev : p.batch;
@@ -84,11 +85,11 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
         if (idx < 0) break;
         // syndrome bits and initialise_log_domain_bp (bp.hpp:147-157)
         const uint32_t *srow = p.synd_packed + idx * p.mwp;
-        for (int i = t; i < m; i += T) {
-            syn[i] = (uint8_t) ((__ldg(srow + (i >> 5)) >> (i & 31)) & 1u);
-            const int deg = UNI ? DC : row_deg[i];
-            for (int k = 0; k < deg; ++k)
-                msg[slot16(row_pos, M, i, k)] = p.uniform_prior ? p.prior0 : prior[slot16(row_col, M, i, k)];
+        for (int w = t; w < p.MW; w += T) synw[w] = __ldg(srow + w);
+        for (int j = t; j < n; j += T) {
+            const int deg = UNI ? DV : col_deg[j];
+            const double pr = p.uniform_prior ? p.prior0 : prior[j];
+            for (int k = 0; k < deg; ++k) msg[slot16(col_pos, N, j, k)] = pr;
         }
         group_sync(bar, T);
 
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
             ++it;
             const double alpha = ms_alpha(p.ms_scaling, it);
             // ---- check -> bit, one thread per row (bp.hpp:201-273) ----
+            for (int w = t; w < p.MW; w += T) acc[w] = synw[w];  // candidate ^ syndrome, must end up all zero
             for (int i = t; i < m; i += T) {
                 const int deg = UNI ? DC : row_deg[i];
                 uint32_t rp[DC];
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
                 }
 #pragma unroll
                 for (int k = 0; k < DC; ++k) b[k] = (k < deg) ? msg[rp[k]] : 0.0;
-                check_node_update<METHOD, DC>(b, deg, (uint32_t) syn[i], alpha, c);
+                check_node_update<METHOD, DC>(b, deg, (synw[i >> 5] >> (i & 31)) & 1u, alpha, c);
 #pragma unroll
                 for (int k = 0; k < DC; ++k)
                     if (k < deg) msg[rp[k]] = c[k];
@@ -138,6 +140,15 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
                         if (k < deg) msg[pos[k]] = c[k];
                     x = (llr <= 0);
                     if (LLR) p.out_llr[idx * n + j] = llr;
+                    if (x) {
+                        // bp.hpp:290-294: a decided-1 bit flips the candidate syndrome of its checks
+#pragma unroll
+                        for (int k = 0; k < DV; ++k)
+                            if (k < deg) {
+                                const uint32_t r = slot16(col_row, N, j, k);
+                                atomicXor(&acc[r >> 5], 1u << (r & 31));
+                            }
+                    }
                 }
                 if (j0 + (t & ~31) < N) {
                     const uint32_t word = __ballot_sync(0xffffffffu, x);
@@ -147,20 +158,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
             group_sync(bar, T);
             // ---- candidate syndrome == syndrome ?  (bp.hpp:292-308) ----
             uint32_t bad = 0;
-            for (int i = t; i < m; i += T) {
-                uint32_t par = syn[i];
-                const int deg = UNI ? DC : row_deg[i];
-#pragma unroll
-                for (int q = 0; q < (DC + 1) / 2; ++q) {
-                    if (2 * q < deg) {
-                        const uint32_t w = row_col[q * M + i];
-                        const uint32_t c0 = w & 0xffffu, c1 = w >> 16;
-                        par ^= dec[c0 >> 5] >> (c0 & 31);
-                        if (2 * q + 1 < deg) par ^= dec[c1 >> 5] >> (c1 & 31);
-                    }
-                }
-                bad |= par & 1u;
-            }
+            for (int w = t; w < p.MW; w += T) bad |= acc[w];
             conv = !group_any(bar, T, bad != 0);
             if (conv) break;
         }

@@ -7,10 +7,11 @@ namespace bpb {
 struct SmemParams {
     const uint32_t *tab;  // table blob in global memory, copied verbatim to the start of shared memory
     uint32_t tab_bytes;   // multiple of 16
-    uint32_t off_row_deg, off_col_deg, off_row_col, off_row_pos, off_col_pos, off_prior;  // byte offsets inside the blob
+    uint32_t off_row_deg, off_col_deg, off_col_row, off_row_pos, off_col_pos, off_prior;  // byte offsets inside the blob
     uint32_t group_bytes;                                                    // per-group area (multiple of 16)
     uint32_t goff_msg, goff_dec, goff_syn, goff_ctl;                         // byte offsets inside a group area
     int m, n, M, N;       // M, N: padded row / column counts (ELL strides)
+    int MW;               // 32-bit words per syndrome, ceil(m / 32)
     int groups, T;        // thread groups per CTA, threads per group
     int max_iter;
     double ms_scaling;

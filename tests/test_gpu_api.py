@@ -46,3 +46,37 @@ def test_info_reports_native_kernel():
     d.decode(np.array([1, 0, 0, 0]))
     inf = d.info()
     assert inf["launches"] >= 2 and inf["kernel_family"] in (1, 2) and inf["grid"] >= 1
+
+
+@pytest.mark.parametrize("kernel", ["stream", "smem"])
+def test_ragged_and_degenerate_batches(kernel):
+    """Empty batch, one syndrome, a batch that is no multiple of the warp / group size, all-zero syndromes, and a
+    batch with repeated rows: results must be per-row and independent of batch composition."""
+    H = codes.regular_ldpc(120, 3, 6, seed=5)
+    d = BpDecoder(H, error_rate=0.05, max_iter=20, bp_method="ms", ms_scaling_factor=0.625,
+                  input_vector_type="syndrome", kernel=kernel)
+    syn = codes.bsc_syndromes(H, 0.06, 77, seed=2)
+    full = d.decode_batch(syn)
+    its = d.iter_batch.copy()
+    assert d.decode_batch(syn[:0]).shape == (0, 120)
+    one = d.decode_batch(syn[5:6])
+    assert np.array_equal(one[0], full[5]) and d.iter_batch[0] == its[5]
+    for lo, hi in ((0, 33), (10, 77), (31, 32)):
+        assert np.array_equal(d.decode_batch(syn[lo:hi]), full[lo:hi])
+    z = d.decode_batch(np.zeros((3, 60), np.uint8))
+    assert not z.any() and d.converge_batch.all() and (d.iter_batch == 1).all()  # C++ semantics for zero syndromes
+    rep = np.repeat(syn[7:8], 40, axis=0)
+    out = d.decode_batch(rep)
+    assert (out == full[7]).all()
+    # int64 in, int64 out (dtype echo of the batch API)
+    assert d.decode_batch(syn.astype(np.int64)).dtype == np.int64
+
+
+def test_multi_gpu_decoder_single_device():
+    from ldpc_b200.parallel import MultiGpuBpDecoder
+    H = codes.regular_ldpc(120, 3, 6, seed=5)
+    syn = codes.bsc_syndromes(H, 0.06, 500, seed=2)
+    kw = dict(error_rate=0.05, max_iter=20, bp_method="ms", ms_scaling_factor=0.625, input_vector_type="syndrome")
+    want = BpDecoder(H, **kw).decode_batch(syn)
+    multi = MultiGpuBpDecoder(H, devices=[0, 0], **kw)  # two handles on the same device: exercises the threaded split
+    assert np.array_equal(multi.decode_batch(syn), want)
