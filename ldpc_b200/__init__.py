@@ -7,6 +7,7 @@ done by hand-written sm_100a CUDA kernels in ``ldpc_b200/csrc`` behind the C-ABI
 from .bp_decoder import BpDecoder, BpDecoderBase, io_test
 from .bposd_decoder import BpOsdDecoder
 from . import codes
+from .monte_carlo import MonteCarloBscSimulation
 
-__all__ = ["BpDecoder", "BpDecoderBase", "BpOsdDecoder", "io_test", "codes"]
+__all__ = ["BpDecoder", "BpDecoderBase", "BpOsdDecoder", "MonteCarloBscSimulation", "io_test", "codes"]
 __version__ = "0.1.0"

@@ -282,7 +282,7 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     if ((rc = ensure(h, h->counter, 64))) return rc;
     BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
     // second stage for the ramp-down (parallel schedule, when the thread-group kernels can take the code)
-    const bool second_stage = h->schedule == BPB_PARALLEL && h->smem_plan.ok && h->max_iter > 16;
+    const bool second_stage = h->smem_plan.ok && h->max_iter > 16;
     if (second_stage && (rc = ensure(h, h->handoff, (size_t) warps * 32 * sizeof(uint32_t)))) return rc;
     p.iter_cap = second_stage ? 12 : h->max_iter + 1;
     p.handoff_count = (unsigned long long *) h->counter.ptr + 1;
@@ -369,6 +369,53 @@ void build_smem_plan(bpb_decoder *h) {
     off += 4u * (uint32_t) (DCp * M);
     pl.off_col_pos = off;
     off += 4u * (uint32_t) (DVp * N);
+    // serial schedule: slot of every edge inside its row, and the levelised schedule
+    pl.serial = (h->schedule == BPB_SERIAL);
+    if (h->serial_order.empty()) {
+        h->serial_order.resize((size_t) g.n);
+        for (int j = 0; j < g.n; j++) h->serial_order[(size_t) j] = (uint32_t) j;
+    }
+    std::vector<uint16_t> lev_ptr, lev_bits;
+    if (pl.serial) {
+        if (h->serial_order.size() > 65535) {
+            pl.why = "serial schedule longer than 65535 entries";
+            return;
+        }
+        std::vector<int> last_level((size_t) g.m, 0), level(h->serial_order.size(), 0);
+        int max_level = 0;
+        for (size_t q = 0; q < h->serial_order.size(); q++) {
+            const uint32_t j = h->serial_order[q];
+            int lv = 0;
+            for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) lv = std::max(lv, last_level[g.row_idx[e]]);
+            lv += 1;
+            for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) last_level[g.row_idx[e]] = lv;
+            level[q] = lv;
+            max_level = std::max(max_level, lv);
+        }
+        lev_ptr.assign((size_t) max_level + 1, 0);
+        for (size_t q = 0; q < level.size(); q++) lev_ptr[(size_t) level[q]]++;  // counts at index level (1-based)
+        // exclusive prefix: lev_ptr[l] = first position of level l+1
+        uint16_t run = 0;
+        for (int l = 1; l <= max_level; l++) {
+            const uint16_t cnt = lev_ptr[(size_t) l];
+            lev_ptr[(size_t) l - 1] = run;
+            run = (uint16_t) (run + cnt);
+        }
+        lev_ptr[(size_t) max_level] = run;
+        lev_bits.resize(level.size());
+        std::vector<uint16_t> fill(lev_ptr.begin(), lev_ptr.end());
+        for (size_t q = 0; q < level.size(); q++) lev_bits[fill[(size_t) level[q] - 1]++] = (uint16_t) h->serial_order[q];
+        pl.n_levels = max_level;
+        pl.mean_level = max_level ? (int) (level.size() / (size_t) max_level) : 0;
+        pl.off_col_self = off;
+        off += (uint32_t) (DVm * N);
+        off = align_up(off, 4);
+        pl.off_lev_ptr = off;
+        off += 2u * (uint32_t) lev_ptr.size();
+        off = align_up(off, 4);
+        pl.off_lev_bits = off;
+        off += 2u * (uint32_t) lev_bits.size();
+    }
     off = align_up(off, 8);
     pl.off_prior = off;
     if (!h->uniform_prior) off += 8u * (uint32_t) g.n;
@@ -446,6 +493,15 @@ void build_smem_plan(bpb_decoder *h) {
             row_pos[2 * ((size_t) (k / 2) * M + i) + (k & 1)] = (uint16_t) slot_of_edge[q];
         }
     }
+    if (pl.serial) {
+        std::memcpy(pl.blob.data() + pl.off_lev_ptr, lev_ptr.data(), 2 * lev_ptr.size());
+        std::memcpy(pl.blob.data() + pl.off_lev_bits, lev_bits.data(), 2 * lev_bits.size());
+        uint8_t *col_self = pl.blob.data() + pl.off_col_self;
+        for (int j = 0; j < g.n; j++)
+            for (uint32_t q = g.col_ptr[(size_t) j]; q < g.col_ptr[(size_t) j + 1]; q++)
+                col_self[(size_t) (q - g.col_ptr[(size_t) j]) * N + j] =
+                    (uint8_t) (g.csc2csr[q] - g.row_ptr[g.row_idx[q]]);
+    }
     for (int j = 0; j < g.n; j++) {
         const uint32_t b = g.col_ptr[(size_t) j], e = g.col_ptr[(size_t) j + 1];
         col_deg[j] = (uint8_t) (e - b);
@@ -474,7 +530,7 @@ void build_smem_plan(bpb_decoder *h) {
     pl.goff_msg = go;
     go += 8u * (uint32_t) pl.msg_doubles;
     pl.goff_dec = go;
-    go += (uint32_t) N / 8;  // one bit per column
+    go += pl.serial ? (uint32_t) N : (uint32_t) N / 8;  // parallel: one bit per column; serial: one byte
     pl.goff_syn = go;
     go += 2u * 4u * (uint32_t) ((g.m + 31) / 32);  // packed syndrome + candidate accumulator
     go = align_up(go, 8);
@@ -488,7 +544,10 @@ void build_smem_plan(bpb_decoder *h) {
     pl.ok = true;
 }
 
-bpb::SmemKernel pick_smem(int method, int dc, int dv, bool regular, bool llr) {
+bpb::SmemKernel pick_smem(int method, int schedule, int dc, int dv, bool regular, bool llr) {
+    if (schedule == BPB_SERIAL)
+        return method == BPB_MINIMUM_SUM ? bpb::pick_smem_serial_ms(dc, dv, regular, llr)
+                                         : bpb::pick_smem_serial_ps(dc, dv, regular, llr);
     if (method == BPB_MINIMUM_SUM) return bpb::pick_smem_ms(dc, dv, regular, llr);
     return bpb::pick_smem_ps(dc, dv, regular, llr);
 }
@@ -499,12 +558,13 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     const bpb::HostGraph &g = h->g;
     const bpb::SmemPlan &pl = h->smem_plan;
     const bool llr = d_llr != nullptr;
-    bpb::SmemKernel k = pick_smem(h->method, g.max_row_degree, g.max_col_degree, g.regular, llr);
-    if (!k || !pl.ok) {
+    bpb::SmemKernel k = pick_smem(h->method, h->schedule, g.max_row_degree, g.max_col_degree, g.regular, llr);
+    if (!k || !pl.ok || pl.serial != (h->schedule == BPB_SERIAL)) {
         h->err = "on-chip kernel family not available for this code: " + pl.why;
         return BPB_ERR_UNSUPPORTED;
     }
-    const int maxt = bpb::smem_cta_threads(h->method, g.max_row_degree, g.max_col_degree);
+    const bool serial = h->schedule == BPB_SERIAL;
+    const int maxt = serial ? 512 : bpb::smem_cta_threads(h->method, g.max_row_degree, g.max_col_degree);
     const size_t tab = pl.blob.size();
     int G = (int) (((size_t) h->max_smem_optin - tab) / pl.group_bytes);
     G = std::min(G, 15);
@@ -514,8 +574,10 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
         T = 32;
         G = maxt / 32;
     }
-    const int want = std::max(32, (int) align_up((uint32_t) std::max(g.m, (g.n + 1) / 2), 32));
-    T = std::min(T, std::min(want, 256));
+    // parallel: a thread per row / two columns; serial: a thread per bit of a level
+    const int want = serial ? std::max(32, (int) align_up((uint32_t) std::max(pl.mean_level, 1), 32))
+                            : std::max(32, (int) align_up((uint32_t) std::max(g.m, (g.n + 1) / 2), 32));
+    T = std::min(T, std::min(want, serial ? 128 : 256));
     const int block = G * T;
     const size_t smem_bytes = tab + (size_t) G * pl.group_bytes;
     BPB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes));
@@ -535,6 +597,10 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.off_row_pos = pl.off_row_pos;
     p.off_col_pos = pl.off_col_pos;
     p.off_prior = pl.off_prior;
+    p.off_col_self = pl.off_col_self;
+    p.off_lev_ptr = pl.off_lev_ptr;
+    p.off_lev_bits = pl.off_lev_bits;
+    p.n_levels = pl.n_levels;
     p.group_bytes = pl.group_bytes;
     p.goff_msg = pl.goff_msg;
     p.goff_dec = pl.goff_dec;
@@ -724,6 +790,7 @@ int bpb_set_schedule(bpb_decoder *h, int v) {
         h->err = "Invalid BP schedule";  // bp.hpp:171
         return v == 2 ? BPB_ERR_UNSUPPORTED : BPB_ERR_ARG;
     }
+    if (h->schedule != v) h->graph_dirty = true;  // the shared-memory plan depends on the schedule
     h->schedule = v;
     return BPB_OK;
 }
@@ -796,13 +863,18 @@ int bpb_decode_batch_device(bpb_decoder *h, int input_type, const uint8_t *d_inp
     h->launches += 1;
     // family: the on-chip kernels serve the parallel schedule of codes whose messages fit in shared memory;
     // everything else (serial schedule, large codes) streams its messages through HBM.
-    const bool smem_able = h->smem_plan.ok && h->schedule == BPB_PARALLEL;
+    const bool smem_able = h->smem_plan.ok;
     if (h->kernel_pref == BPB_KERNEL_SMEM && !smem_able) {
-        h->err = "kernel family 'smem' requested but not available: " +
-                 (h->schedule != BPB_PARALLEL ? std::string("serial schedule") : h->smem_plan.why);
+        h->err = "kernel family 'smem' requested but not available: " + h->smem_plan.why;
         return BPB_ERR_UNSUPPORTED;
     }
-    if (smem_able && h->kernel_pref != BPB_KERNEL_STREAM)
+    // AUTO: the thread-group kernels win for the parallel schedule (3x the streaming family at n = 1000); for the
+    // serial schedule the levelised streaming kernel measured slightly faster (6.5 vs 5.8 M decodes/s at n = 1000,
+    // a level has only ~n/30 independent bits), so the on-chip serial kernel serves as its ramp-down second stage
+    // and on request (kernel = smem).
+    const bool use_smem = smem_able && (h->kernel_pref == BPB_KERNEL_SMEM ||
+                                        (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
+    if (use_smem)
         rc = launch_smem(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st, nullptr, nullptr);
     else
         rc = launch_stream(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st);
@@ -833,7 +905,8 @@ int bpb_decode_batch(bpb_decoder *h, int input_type, const uint8_t *input, int64
     // Chunked three-stage pipeline (H2D | kernels | D2H) over two staging slots.  The on-chip family keeps no
     // per-lane state in HBM, so small chunks cost nothing; the streaming family amortises its persistent-lane
     // ramp-down over large chunks.
-    const bool smem_able = h->smem_plan.ok && h->schedule == BPB_PARALLEL && h->kernel_pref != BPB_KERNEL_STREAM;
+    const bool smem_able = h->smem_plan.ok && (h->kernel_pref == BPB_KERNEL_SMEM ||
+                                               (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
     const int64_t chunk_max = smem_able ? ((int64_t) 1 << 17) : ((int64_t) 1 << 20);
     int64_t c = 0;
     for (int64_t lo = 0; lo < batch; lo += chunk_max, ++c) {

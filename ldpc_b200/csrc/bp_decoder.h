@@ -38,6 +38,9 @@ struct SmemPlan {
     std::string why;            // why the family is not usable for this code (when !ok)
     std::vector<uint8_t> blob;  // tables in their final shared-memory byte layout
     uint32_t off_row_deg = 0, off_col_deg = 0, off_col_row = 0, off_row_pos = 0, off_col_pos = 0, off_prior = 0;
+    bool serial = false;        // built for the serial schedule (extra tables: self slots, levels)
+    uint32_t off_col_self = 0, off_lev_ptr = 0, off_lev_bits = 0;
+    int n_levels = 0, mean_level = 0;
     int max_bank_multiplicity = 0;  // 1 = both passes conflict-free (verified by build_smem_plan)
     int msg_doubles = 0;        // length of one group's message array (16 * largest colour class)
     uint32_t group_bytes = 0, goff_msg = 0, goff_dec = 0, goff_syn = 0, goff_ctl = 0;

@@ -7,7 +7,9 @@ namespace bpb {
 struct SmemParams {
     const uint32_t *tab;  // table blob in global memory, copied verbatim to the start of shared memory
     uint32_t tab_bytes;   // multiple of 16
-    uint32_t off_row_deg, off_col_deg, off_col_row, off_row_pos, off_col_pos, off_prior;  // byte offsets inside the blob
+    uint32_t off_row_deg, off_col_deg, off_col_row, off_row_pos, off_col_pos, off_prior;
+    uint32_t off_col_self, off_lev_ptr, off_lev_bits;  // serial schedule only (bp_smem_serial.cuh)
+    int n_levels;  // byte offsets inside the blob
     uint32_t group_bytes;                                                    // per-group area (multiple of 16)
     uint32_t goff_msg, goff_dec, goff_syn, goff_ctl;                         // byte offsets inside a group area
     int m, n, M, N;       // M, N: padded row / column counts (ELL strides)
@@ -39,5 +41,8 @@ inline int smem_cta_threads(int method, int dc, int dv) { return (method == 1 &&
 // `regular`: every row has exactly max_row_degree entries and every column exactly max_col_degree
 SmemKernel pick_smem_ms(int max_row_degree, int max_col_degree, bool regular, bool llr);
 SmemKernel pick_smem_ps(int max_row_degree, int max_col_degree, bool regular, bool llr);
+// serial schedule (bp_smem_serial.cuh), always 512-thread CTAs
+SmemKernel pick_smem_serial_ms(int max_row_degree, int max_col_degree, bool regular, bool llr);
+SmemKernel pick_smem_serial_ps(int max_row_degree, int max_col_degree, bool regular, bool llr);
 
 }  // namespace bpb

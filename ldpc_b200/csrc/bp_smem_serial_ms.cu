@@ -1,0 +1,7 @@
+// Instantiates the min-sum on-chip SERIAL-schedule kernels (bp_smem_serial.cuh).
+#include "bp_smem_serial.cuh"
+namespace bpb {
+SmemKernel pick_smem_serial_ms(int dc, int dv, bool regular, bool llr) {
+    return pick_smem_serial_bucket<kMinimumSum>(dc, dv, regular, llr);
+}
+}  // namespace bpb

@@ -14,8 +14,6 @@ FAMILIES = ["stream", "smem"]
 
 
 def _decode_gpu(H, syn, p, kernel="auto", **kw):
-    if kernel == "smem" and kw.get("schedule", "parallel") not in ("parallel", "p", 0):
-        pytest.skip("the on-chip family implements the parallel schedule")
     dec = BpDecoder(H, kernel=kernel, error_channel=np.broadcast_to(np.asarray(p, float), (H.shape[1],)).copy(),
                     input_vector_type="syndrome", **kw)
     out = dec.decode_batch(syn, return_llr=True)
@@ -77,14 +75,15 @@ def test_nonuniform_channel_with_certain_bits(port_oracle, method, kernel):
     assert np.isinf(want[3]).any()
 
 
-def test_custom_serial_order(port_oracle):
+@pytest.mark.parametrize("kernel", FAMILIES)
+def test_custom_serial_order(port_oracle, kernel):
     H = codes.regular_ldpc(200, 3, 6, seed=2)
     order = np.random.default_rng(4).permutation(200)
     syn = codes.bsc_syndromes(H, 0.06, 700, seed=9)
     for method in ("ms", "ps"):
         kw = dict(max_iter=25, bp_method=method, schedule="serial", ms_scaling_factor=0.9)
         want = port_oracle.decode_batch(H, syn, 0.06, serial_schedule_order=order, **kw)
-        got = _decode_gpu(H, syn, 0.06, serial_schedule_order=[int(x) for x in order], **kw)
+        got = _decode_gpu(H, syn, 0.06, kernel=kernel, serial_schedule_order=[int(x) for x in order], **kw)
         assert_same_decode(got, want, llr_exact=(method == "ms"))
 
 
@@ -104,8 +103,6 @@ def test_irregular_degrees(port_oracle, kernel):
     syn = codes.syndromes_of(H, err)
     for method, sched in (("ms", "parallel"), ("ps", "parallel"), ("ms", "serial"), ("ps", "serial")):
         kw = dict(max_iter=15, bp_method=method, schedule=sched, ms_scaling_factor=0.625)
-        if kernel == "smem" and sched == "serial":
-            continue
         want = port_oracle.decode_batch(H, syn, 0.04, **kw)
         assert_same_decode(_decode_gpu(H, syn, 0.04, kernel=kernel, **kw), want, llr_exact=(method == "ms"))
 
@@ -174,8 +171,6 @@ def test_golden_fixtures_from_reference(kernel):
         H = sp.csr_matrix((np.ones(z["rows"].size, np.uint8), (z["rows"], z["cols"])), shape=tuple(z["shape"]))
         kw = dict(max_iter=int(z["max_iter"]), bp_method=str(z["bp_method"]), schedule=str(z["schedule"]),
                   ms_scaling_factor=float(z["ms_scaling_factor"]))
-        if kernel == "smem" and kw["schedule"] != "parallel":
-            continue
         got = _decode_gpu(H, z["syndromes"], z["channel"], kernel=kernel, **kw)
         assert_same_decode(got, (z["decoding"], z["converged"], z["iters"], z["llr"]),
                            llr_exact=(str(z["bp_method"]) == "ms"))

@@ -245,3 +245,35 @@ def test_shared_memory_placement_is_conflict_free(mk):
     assert inf.smem_family_available == 1
     assert inf.smem_bank_multiplicity == 1
     assert inf.smem_bytes_per_syndrome >= 8 * H.nnz
+
+
+def test_monte_carlo_driver_matches_reference_loop(port_oracle):
+    """MonteCarloBscSimulation (batched) against the reference's one-run-at-a-time loop (mcs.py:124-149) with the
+    same seed; the decoder here is a CPU stand-in with a decode_batch method so that the host logic is covered
+    without a GPU."""
+    from ldpc_b200 import MonteCarloBscSimulation
+    H = codes.regular_ldpc(120, 3, 6, seed=5)
+    kw = dict(max_iter=10, bp_method="ms", ms_scaling_factor=0.625)
+
+    class OracleDecoder:
+        def decode_batch(self, syn):
+            return port_oracle.decode_batch(H, syn, 0.08, want_llr=False, **kw)[0]
+
+    sim = MonteCarloBscSimulation(H, error_rate=0.08, Decoder=OracleDecoder(), target_run_count=300, seed=11,
+                                  batch_size=128, tqdm_disable=True)
+    out = sim.run()
+    # reference loop
+    np.random.seed(11)
+    Hs = sp.csr_matrix(H, dtype=np.int32)
+    fails = 0
+    for _ in range(300):
+        err = np.random.binomial(1, 0.08, 120).astype(np.uint8)
+        syn = (Hs @ err % 2).astype(np.uint8)
+        dec = port_oracle.decode_batch(H, syn[None, :], 0.08, want_llr=False, **kw)[0][0]
+        fails += not np.array_equal(dec, err)
+    assert out["run_count"] == 300 and out["fail_count"] == fails and 0 < fails < 300
+    assert abs(out["logical_error_rate"] - fails / 300) < 1e-15
+    with pytest.raises(ValueError):
+        MonteCarloBscSimulation(H, error_rate=1, Decoder=OracleDecoder())
+    with pytest.raises(ValueError):
+        MonteCarloBscSimulation(H, error_rate=0.1, Decoder=None)
