@@ -106,8 +106,9 @@ __global__ void xor_received_kernel(uint8_t *__restrict__ dec, const uint8_t *__
         dec[i] ^= (v[i] != 0);
 }
 
-void build_smem_plan(bpb_decoder *h);
-std::vector<uint32_t> build_serial_batches(const bpb::HostGraph &g, const std::vector<uint32_t> &order, int sb);
+using bpb::build_serial_batches;
+using bpb::build_smem_plan;
+using bpb::compute_priors;
 
 // BP+OSD: gather the posterior LLR rows of the syndromes BP did not solve (one warp per syndrome) so that only
 // those cross PCIe (the reference hands bpd.log_prob_ratios to OSD only when !bpd.converge, _bposd_decoder.pyx:128-134)
@@ -128,17 +129,6 @@ __global__ void compact_failures_kernel(const uint8_t *__restrict__ conv, const 
 }
 
 // ---- graph blob ---------------------------------------------------------------------------------------
-
-void compute_priors(bpb_decoder *h) {
-    const bpb::HostGraph &g = h->g;
-    // priors on the host, the reference's expression (bp.hpp:150-151)
-    h->prior.resize((size_t) g.n);
-    h->uniform_prior = true;
-    for (int j = 0; j < g.n; j++) {
-        h->prior[(size_t) j] = std::log((1 - h->channel[(size_t) j]) / h->channel[(size_t) j]);
-        if (std::memcmp(&h->prior[(size_t) j], &h->prior[0], sizeof(double)) != 0) h->uniform_prior = false;
-    }
-}
 
 int upload_graph(bpb_decoder *h) {
     const bpb::HostGraph &g = h->g;
@@ -210,31 +200,6 @@ StreamKernel pick_stream(int method, int schedule, int dc, int dv, bool reg, boo
     if (method == BPB_MINIMUM_SUM && schedule == BPB_SERIAL) return bpb::pick_stream_ms_serial(dc, dv, reg, llr);
     if (method == BPB_PRODUCT_SUM && schedule == BPB_SERIAL) return bpb::pick_stream_ps_serial(dc, dv, reg, llr);
     return nullptr;
-}
-
-// Levelise the serial schedule (see the serial branch of bp_stream.cuh): level(q) = 1 + max level of the earlier
-// schedule positions whose bit shares a check with this one; stable-sort by level; cut each level into batches of
-// `sb` bits, padding the last batch of a level with 0xffffffff.
-std::vector<uint32_t> build_serial_batches(const bpb::HostGraph &g, const std::vector<uint32_t> &order, int sb) {
-    std::vector<int> last_level((size_t) g.m, 0), level(order.size(), 0);
-    int max_level = 0;
-    for (size_t q = 0; q < order.size(); q++) {
-        const uint32_t j = order[q];
-        int lv = 0;
-        for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) lv = std::max(lv, last_level[g.row_idx[e]]);
-        lv += 1;
-        for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) last_level[g.row_idx[e]] = lv;
-        level[q] = lv;
-        max_level = std::max(max_level, lv);
-    }
-    std::vector<std::vector<uint32_t>> by_level((size_t) max_level + 1);
-    for (size_t q = 0; q < order.size(); q++) by_level[(size_t) level[q]].push_back(order[q]);
-    std::vector<uint32_t> out;
-    for (const auto &bits: by_level) {
-        for (uint32_t j: bits) out.push_back(j);
-        while (out.size() % (size_t) sb) out.push_back(0xffffffffu);
-    }
-    return out;
 }
 
 int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
@@ -335,214 +300,9 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     return BPB_OK;
 }
 
-// ---- on-chip family: shared-memory plan and launch ------------------------------------------------------
+// ---- on-chip family: launch -------------------------------------------------------------------------------
 
 inline uint32_t align_up(uint32_t x, uint32_t q) { return (x + q - 1) / q * q; }
-
-void build_smem_plan(bpb_decoder *h) {
-    const bpb::HostGraph &g = h->g;
-    bpb::SmemPlan &pl = h->smem_plan;
-    pl = bpb::SmemPlan();
-    const int DCm = g.max_row_degree, DVm = g.max_col_degree;
-    const int M = (int) align_up((uint32_t) g.m, 16), N = (int) align_up((uint32_t) g.n, 32);
-    if (DCm > 32 || DVm > 16) {
-        pl.why = "row degree > 32 or column degree > 16";
-        return;
-    }
-    if (DCm < 1 || (int64_t) g.nnz + 16 * 17 > 65535 || g.n > 65535 || g.m > 65535) {
-        pl.why = "message positions do not fit 16-bit indices";
-        return;
-    }
-    pl.M = M;
-    pl.N = N;
-    uint32_t off = 0;
-    pl.off_row_deg = off;
-    off += (uint32_t) M;
-    pl.off_col_deg = off;
-    off += (uint32_t) N;
-    off = align_up(off, 4);
-    // 16-bit entries, two slots (2q, 2q+1) of the same row / column packed into one 32-bit word: tab[q*stride + x]
-    const int DCp = (DCm + 1) / 2, DVp = (DVm + 1) / 2;
-    pl.off_col_row = off;
-    off += 4u * (uint32_t) (DVp * N);
-    pl.off_row_pos = off;
-    off += 4u * (uint32_t) (DCp * M);
-    pl.off_col_pos = off;
-    off += 4u * (uint32_t) (DVp * N);
-    // serial schedule: slot of every edge inside its row, and the levelised schedule
-    pl.serial = (h->schedule == BPB_SERIAL);
-    if (h->serial_order.empty()) {
-        h->serial_order.resize((size_t) g.n);
-        for (int j = 0; j < g.n; j++) h->serial_order[(size_t) j] = (uint32_t) j;
-    }
-    std::vector<uint16_t> lev_ptr, lev_bits;
-    if (pl.serial) {
-        if (h->serial_order.size() > 65535) {
-            pl.why = "serial schedule longer than 65535 entries";
-            return;
-        }
-        std::vector<int> last_level((size_t) g.m, 0), level(h->serial_order.size(), 0);
-        int max_level = 0;
-        for (size_t q = 0; q < h->serial_order.size(); q++) {
-            const uint32_t j = h->serial_order[q];
-            int lv = 0;
-            for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) lv = std::max(lv, last_level[g.row_idx[e]]);
-            lv += 1;
-            for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) last_level[g.row_idx[e]] = lv;
-            level[q] = lv;
-            max_level = std::max(max_level, lv);
-        }
-        lev_ptr.assign((size_t) max_level + 1, 0);
-        for (size_t q = 0; q < level.size(); q++) lev_ptr[(size_t) level[q]]++;  // counts at index level (1-based)
-        // exclusive prefix: lev_ptr[l] = first position of level l+1
-        uint16_t run = 0;
-        for (int l = 1; l <= max_level; l++) {
-            const uint16_t cnt = lev_ptr[(size_t) l];
-            lev_ptr[(size_t) l - 1] = run;
-            run = (uint16_t) (run + cnt);
-        }
-        lev_ptr[(size_t) max_level] = run;
-        lev_bits.resize(level.size());
-        std::vector<uint16_t> fill(lev_ptr.begin(), lev_ptr.end());
-        for (size_t q = 0; q < level.size(); q++) lev_bits[fill[(size_t) level[q] - 1]++] = (uint16_t) h->serial_order[q];
-        pl.n_levels = max_level;
-        pl.mean_level = max_level ? (int) (level.size() / (size_t) max_level) : 0;
-        pl.off_col_self = off;
-        off += (uint32_t) (DVm * N);
-        off = align_up(off, 4);
-        pl.off_lev_ptr = off;
-        off += 2u * (uint32_t) lev_ptr.size();
-        off = align_up(off, 4);
-        pl.off_lev_bits = off;
-        off += 2u * (uint32_t) lev_bits.size();
-    }
-    off = align_up(off, 8);
-    pl.off_prior = off;
-    if (!h->uniform_prior) off += 8u * (uint32_t) g.n;
-    off = align_up(off, 16);
-    pl.blob.assign(off, 0);
-    uint8_t *row_deg = pl.blob.data() + pl.off_row_deg;
-    uint8_t *col_deg = pl.blob.data() + pl.off_col_deg;
-    uint16_t *col_row = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_row);
-    uint16_t *row_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_row_pos);
-    uint16_t *col_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_pos);
-    // Message placement.  Every message is written by one thread and read by another: row threads touch it in the
-    // check pass (half-warp = 16 consecutive rows, same slot k), column threads in the bit pass (16 consecutive
-    // columns, same slot).  An 8-byte shared-memory access is served per half-warp and is conflict-free iff the 16
-    // lanes hit 16 different bank pairs.  Take the bipartite multigraph whose left nodes are the (row group, slot)
-    // cells, right nodes the (column group, slot) cells and whose edges are the nonzeros of H: every node has degree
-    // <= 16, so by Koenig's theorem its edges can be coloured with 16 colours such that no two edges at a node share
-    // a colour.  Colour = bank pair: both passes become conflict-free.  (Alternating-path edge colouring below.)
-    const int n_rc = ((g.m + 15) / 16) * DCm, n_cc = ((g.n + 15) / 16) * DVm;
-    std::vector<int> edge_rc((size_t) g.nnz), edge_cc((size_t) g.nnz), colour((size_t) g.nnz, -1);
-    std::vector<int> at_r((size_t) n_rc * 16, -1), at_c((size_t) n_cc * 16, -1);  // edge using colour q at the node
-    for (int i = 0; i < g.m; i++)
-        for (uint32_t q = g.row_ptr[(size_t) i]; q < g.row_ptr[(size_t) i + 1]; q++)
-            edge_rc[q] = (i / 16) * DCm + (int) (q - g.row_ptr[(size_t) i]);
-    for (int j = 0; j < g.n; j++)
-        for (uint32_t q = g.col_ptr[(size_t) j]; q < g.col_ptr[(size_t) j + 1]; q++)
-            edge_cc[g.csc2csr[q]] = (j / 16) * DVm + (int) (q - g.col_ptr[(size_t) j]);
-    for (int e = 0; e < g.nnz; e++) {
-        const int u = edge_rc[(size_t) e], v = edge_cc[(size_t) e];
-        int a = 0, b = 0;
-        while (at_r[(size_t) u * 16 + a] >= 0) a++;  // free at u (exists: degree <= 16 and e itself uncoloured)
-        while (at_c[(size_t) v * 16 + b] >= 0) b++;  // free at v
-        if (a != b) {
-            // walk the a/b alternating path that starts at v with colour a and swap a <-> b along it; it cannot
-            // reach u (bipartite, a is free at u), so afterwards a is free at both ends
-            std::vector<int> path;
-            int node = v, want = a;
-            bool on_col_side = true;
-            for (;;) {
-                const int f = on_col_side ? at_c[(size_t) node * 16 + want] : at_r[(size_t) node * 16 + want];
-                if (f < 0) break;
-                path.push_back(f);
-                node = on_col_side ? edge_rc[(size_t) f] : edge_cc[(size_t) f];
-                on_col_side = !on_col_side;
-                want = (want == a) ? b : a;
-            }
-            for (int f: path) {
-                at_r[(size_t) edge_rc[(size_t) f] * 16 + colour[(size_t) f]] = -1;
-                at_c[(size_t) edge_cc[(size_t) f] * 16 + colour[(size_t) f]] = -1;
-            }
-            for (int f: path) {
-                colour[(size_t) f] = (colour[(size_t) f] == a) ? b : a;
-                at_r[(size_t) edge_rc[(size_t) f] * 16 + colour[(size_t) f]] = f;
-                at_c[(size_t) edge_cc[(size_t) f] * 16 + colour[(size_t) f]] = f;
-            }
-        }
-        colour[(size_t) e] = a;
-        at_r[(size_t) u * 16 + a] = e;
-        at_c[(size_t) v * 16 + a] = e;
-    }
-    int per_colour[16] = {0};
-    std::vector<uint32_t> slot_of_edge((size_t) g.nnz);
-    for (int e = 0; e < g.nnz; e++) slot_of_edge[(size_t) e] = (uint32_t) (colour[(size_t) e] + 16 * per_colour[colour[(size_t) e]]++);
-    int longest = 0;
-    for (int q = 0; q < 16; q++) longest = std::max(longest, per_colour[q]);
-    pl.msg_doubles = 16 * longest;
-    if (pl.msg_doubles > 65535) {
-        pl.why = "message positions do not fit 16-bit indices";
-        return;
-    }
-    for (int i = 0; i < g.m; i++) {
-        const uint32_t b = g.row_ptr[(size_t) i], e = g.row_ptr[(size_t) i + 1];
-        row_deg[i] = (uint8_t) (e - b);
-        for (uint32_t q = b; q < e; q++) {
-            const uint32_t k = q - b;
-            row_pos[2 * ((size_t) (k / 2) * M + i) + (k & 1)] = (uint16_t) slot_of_edge[q];
-        }
-    }
-    if (pl.serial) {
-        std::memcpy(pl.blob.data() + pl.off_lev_ptr, lev_ptr.data(), 2 * lev_ptr.size());
-        std::memcpy(pl.blob.data() + pl.off_lev_bits, lev_bits.data(), 2 * lev_bits.size());
-        uint8_t *col_self = pl.blob.data() + pl.off_col_self;
-        for (int j = 0; j < g.n; j++)
-            for (uint32_t q = g.col_ptr[(size_t) j]; q < g.col_ptr[(size_t) j + 1]; q++)
-                col_self[(size_t) (q - g.col_ptr[(size_t) j]) * N + j] =
-                    (uint8_t) (g.csc2csr[q] - g.row_ptr[g.row_idx[q]]);
-    }
-    for (int j = 0; j < g.n; j++) {
-        const uint32_t b = g.col_ptr[(size_t) j], e = g.col_ptr[(size_t) j + 1];
-        col_deg[j] = (uint8_t) (e - b);
-        for (uint32_t q = b; q < e; q++) {
-            col_pos[2 * ((size_t) ((q - b) / 2) * N + j) + ((q - b) & 1)] = (uint16_t) slot_of_edge[g.csc2csr[q]];
-            col_row[2 * ((size_t) ((q - b) / 2) * N + j) + ((q - b) & 1)] = (uint16_t) g.row_idx[q];
-        }
-    }
-    // verify: largest number of lanes of one half-warp access that share a bank pair (1 = conflict-free)
-    pl.max_bank_multiplicity = 0;
-    for (int pass = 0; pass < 2; pass++) {
-        const int items = pass == 0 ? g.m : g.n, stride = pass == 0 ? M : N, slots = pass == 0 ? DCm : DVm;
-        const uint16_t *tab = pass == 0 ? row_pos : col_pos;
-        const uint8_t *deg = pass == 0 ? row_deg : col_deg;
-        for (int base = 0; base < items; base += 16)
-            for (int k = 0; k < slots; k++) {
-                int cnt[16] = {0};
-                for (int x = base; x < std::min(items, base + 16); x++)
-                    if (k < deg[x])
-                        pl.max_bank_multiplicity = std::max(
-                            pl.max_bank_multiplicity, ++cnt[tab[2 * ((size_t) (k / 2) * stride + x) + (k & 1)] & 15]);
-            }
-    }
-    if (!h->uniform_prior) std::memcpy(pl.blob.data() + pl.off_prior, h->prior.data(), 8 * (size_t) g.n);
-    uint32_t go = 0;
-    pl.goff_msg = go;
-    go += 8u * (uint32_t) pl.msg_doubles;
-    pl.goff_dec = go;
-    go += pl.serial ? (uint32_t) N : (uint32_t) N / 8;  // parallel: one bit per column; serial: one byte
-    pl.goff_syn = go;
-    go += 2u * 4u * (uint32_t) ((g.m + 31) / 32);  // packed syndrome + candidate accumulator
-    go = align_up(go, 8);
-    pl.goff_ctl = go;
-    go += 8;
-    pl.group_bytes = align_up(go, 16);
-    if ((size_t) off + pl.group_bytes > (size_t) h->max_smem_optin) {
-        pl.why = "one syndrome's messages do not fit in shared memory";
-        return;
-    }
-    pl.ok = true;
-}
 
 bpb::SmemKernel pick_smem(int method, int schedule, int dc, int dv, bool regular, bool llr) {
     if (schedule == BPB_SERIAL)

@@ -49,6 +49,15 @@ struct SmemPlan {
 
 }  // namespace bpb
 
+struct bpb_decoder;
+
+namespace bpb {
+// bp_plan.cpp (host-only planning)
+void compute_priors(bpb_decoder *h);
+std::vector<uint32_t> build_serial_batches(const HostGraph &g, const std::vector<uint32_t> &order, int sb);
+void build_smem_plan(bpb_decoder *h);
+}  // namespace bpb
+
 struct bpb_decoder {
     bpb::HostGraph g;
     int device = 0;
