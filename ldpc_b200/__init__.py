@@ -8,6 +8,8 @@ from .bp_decoder import BpDecoder, BpDecoderBase, io_test
 from .bposd_decoder import BpOsdDecoder
 from . import codes
 from .monte_carlo import MonteCarloBscSimulation
+from .legacy import bp_decoder, bposd_decoder
 
-__all__ = ["BpDecoder", "BpDecoderBase", "BpOsdDecoder", "MonteCarloBscSimulation", "io_test", "codes"]
+__all__ = ["BpDecoder", "BpDecoderBase", "BpOsdDecoder", "MonteCarloBscSimulation", "bp_decoder", "bposd_decoder",
+           "io_test", "codes"]
 __version__ = "0.1.0"

@@ -80,3 +80,30 @@ def test_multi_gpu_decoder_single_device():
     want = BpDecoder(H, **kw).decode_batch(syn)
     multi = MultiGpuBpDecoder(H, devices=[0, 0], **kw)  # two handles on the same device: exercises the threaded split
     assert np.array_equal(multi.decode_batch(syn), want)
+
+
+def test_v1_vs_v2_same_logical_error_rate():
+    """reference python_test/test_bp_decoder.py:238-263: rep_code(100), min-sum, 10 iterations, 1000 seeded runs --
+    the v1-syntax class and the v2 class give the same logical error rate (here both through decode_batch)."""
+    import warnings
+    from ldpc_b200 import MonteCarloBscSimulation, bp_decoder
+    H = codes.rep_code(100)
+    bpd = BpDecoder(H, error_rate=0.20, bp_method="ms", schedule="parallel", ms_scaling_factor=1.0, max_iter=10)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bpd_v1 = bp_decoder(H, error_rate=0.20, bp_method="ms", ms_scaling_factor=1.0, max_iter=10)
+    out1 = MonteCarloBscSimulation(H, error_rate=0.20, Decoder=bpd, target_run_count=1000, seed=42).run()
+    out2 = MonteCarloBscSimulation(H, error_rate=0.20, Decoder=bpd_v1, target_run_count=1000, seed=42).run()
+    assert out1["logical_error_rate"] == out2["logical_error_rate"]
+    assert 0 < out1["fail_count"] < 1000
+
+
+def test_unsupported_degree_fails_loudly():
+    dense = np.zeros((3, 60), np.uint8)
+    dense[0, :40] = 1  # a check of degree 40 > 32
+    dense[1, 30:] = 1
+    dense[2, ::2] = 1
+    d = BpDecoder(dense, error_rate=0.05, max_iter=3, bp_method="ms", input_vector_type="syndrome")
+    with pytest.raises(Exception) as e:
+        d.decode_batch(np.ones((4, 3), np.uint8))
+    assert "degree" in str(e.value)

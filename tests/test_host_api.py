@@ -277,3 +277,22 @@ def test_monte_carlo_driver_matches_reference_loop(port_oracle):
         MonteCarloBscSimulation(H, error_rate=1, Decoder=OracleDecoder())
     with pytest.raises(ValueError):
         MonteCarloBscSimulation(H, error_rate=0.1, Decoder=None)
+
+
+def test_legacy_v1_constructors():
+    # python_test/test_bp_decoder_input.py: the v1 classes accept ndarray / csr / csc and v1 argument names
+    from ldpc_b200 import bp_decoder, bposd_decoder
+    dense = codes.hamming_code(3).toarray()
+    for mat in (dense, sp.csr_matrix(dense), sp.csc_matrix(dense)):
+        with pytest.warns(UserWarning):
+            d = bp_decoder(mat, error_rate=0.1, bp_method="min_sum", ms_scaling_factor=1, max_iter=4)
+        assert d.bp_method == "minimum_sum" and d.max_iter == 4 and d.ms_scaling_factor == 1.0
+        with pytest.warns(UserWarning):
+            o = bposd_decoder(mat, channel_probs=[0.1] * 7, bp_method="ps", osd_method="osd_0")
+        assert o.osd_method == "OSD_0" and np.allclose(o.channel_probs, 0.1)
+    with pytest.warns(UserWarning), pytest.raises(ValueError):
+        bp_decoder(dense, channel_probs=[0.1, 0.2])
+    with pytest.warns(UserWarning), pytest.raises(ValueError):
+        bp_decoder(dense, error_rate=0)
+    with pytest.warns(UserWarning), pytest.raises(ValueError):
+        bposd_decoder(dense, error_rate=0.1, osd_method="bogus")
