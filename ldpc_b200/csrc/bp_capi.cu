@@ -212,10 +212,10 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     const bool llr = d_llr != nullptr;
     StreamKernel k = pick_stream(h->method, h->schedule, g.max_row_degree, g.max_col_degree, g.regular, llr);
     if (!k) {
-        h->err = "stream kernels support row degree <= 32 and column degree <= 16 (got " +
-                 std::to_string(g.max_row_degree) + ", " + std::to_string(g.max_col_degree) + ")";
+        h->err = "no streaming kernel for this configuration";
         return BPB_ERR_UNSUPPORTED;
     }
+    const bool generic = g.max_row_degree > 32 || g.max_col_degree > 16;  // two message arrays per tile
     const int block = 256, wpb = block / 32;
     const int m_pad = round_up(g.m, 32), n_pad = round_up(g.n, 32);
     const size_t blob_bytes = (size_t) h->blob_words * 4;
@@ -240,7 +240,7 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     const int grid = (int) grid64;
     const size_t warps = (size_t) grid * wpb;
     int rc;
-    if ((rc = ensure(h, h->msg, warps * (size_t) g.nnz * 32 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->msg, warps * (size_t) g.nnz * 32 * sizeof(double) * (generic ? 2 : 1)))) return rc;
     if ((rc = ensure(h, h->dec_w, warps * (size_t) n_pad * 4, true, st))) return rc;
     if ((rc = ensure(h, h->syn_w, p.smem_syn ? 16 : warps * (size_t) m_pad * 4, true, st))) return rc;
     if (llr && (rc = ensure(h, h->llr_tile, warps * (size_t) g.n * 32 * sizeof(double)))) return rc;

@@ -58,7 +58,12 @@ __global__ void __launch_bounds__(256, (SCHED == kParallel && DC <= 8 && DV <= 4
 
     uint32_t *syn_w = p.smem_syn ? (smem + p.smem_syn_off + (size_t) wib * p.m_pad) : (p.syn_w_g + gw * p.m_pad);
     uint32_t *dec_w = p.dec_w + gw * p.n_pad;
-    double *tile = p.msg + (size_t) gw * (size_t) nnz * 32 + lane;
+    // GEN (DC == 0): any degree.  The reference's own two-array scheme (b2c at tile, c2b behind it), its two sweeps
+    // per row / column with running values instead of register arrays (bp.hpp:201-318, 484-534 literally).
+    constexpr bool GEN = (DC == 0);
+    double *tile = p.msg + (size_t) gw * (size_t) nnz * 32 * (GEN ? 2 : 1) + lane;
+    double *c2b = tile + (size_t) nnz * 32;  // GEN only
+    (void) c2b;
     double *llr_tile = LLR ? (p.llr_tile + (size_t) gw * (size_t) n * 32 + lane) : nullptr;
 
     long long idx = -1;  // syndrome this lane is decoding, -1 = idle
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(256, (SCHED == kParallel && DC <= 8 && DV <= 4
                     const int i = w * 32 + lane;
                     if (i < m) syn_w[i] = (syn_w[i] & ~newmask) | (mine_w & newmask);
                 }
-                if (SCHED == kSerial) {
+                if (SCHED == kSerial || GEN) {
                     // explicit initialise_log_domain_bp (bp.hpp:147-157) for the new lanes
                     if (fresh)
                         for (int e = 0; e < nnz; ++e)
@@ -117,6 +122,123 @@ __global__ void __launch_bounds__(256, (SCHED == kParallel && DC <= 8 && DV <= 4
         (void) alpha;
         (void) any_first;
 
+        if constexpr (GEN) {
+            if (SCHED == kParallel) {
+                for (int i = 0; i < m; ++i) {  // bp.hpp:201-273, two sweeps per row
+                    const uint32_t rb = row_ptr[i], re = row_ptr[i + 1];
+                    const uint32_t s = (syn_w[i] >> lane) & 1u;
+                    if (METHOD == kMinimumSum) {
+                        uint32_t tsgn = s;
+                        double temp = DBL_MAX;
+                        for (uint32_t e = rb; e < re; ++e) {
+                            const double b = active ? ld_msg(tile + (size_t) e * 32) : 0.0;
+                            if (b <= 0) tsgn += 1;
+                            if (active) st_msg(c2b + (size_t) e * 32, temp);
+                            const double a = fabs(b);
+                            if (a < temp) temp = a;
+                        }
+                        temp = DBL_MAX;
+                        for (uint32_t e = re; e-- > rb;) {
+                            const double b = active ? ld_msg(tile + (size_t) e * 32) : 0.0;
+                            double c = active ? ld_msg(c2b + (size_t) e * 32) : 0.0;
+                            const uint32_t sg = tsgn + ((b <= 0) ? 1u : 0u);
+                            if (temp < c) c = temp;
+                            c *= (sg & 1u) ? -alpha : alpha;
+                            if (active) st_msg(c2b + (size_t) e * 32, c);
+                            const double a = fabs(b);
+                            if (a < temp) temp = a;
+                        }
+                    } else {
+                        double temp = 1.0;
+                        for (uint32_t e = rb; e < re; ++e) {
+                            const double b = active ? ld_msg(tile + (size_t) e * 32) : 0.0;
+                            if (active) st_msg(c2b + (size_t) e * 32, temp);
+                            temp *= ps_tanh_half(b);
+                        }
+                        temp = 1.0;
+                        const double sigma = s ? -1.0 : 1.0;
+                        for (uint32_t e = re; e-- > rb;) {
+                            const double b = active ? ld_msg(tile + (size_t) e * 32) : 0.0;
+                            double c = active ? ld_msg(c2b + (size_t) e * 32) : 0.0;
+                            c *= temp;
+                            c = sigma * ps_atanh2(c);
+                            if (active) st_msg(c2b + (size_t) e * 32, c);
+                            temp *= ps_tanh_half(b);
+                        }
+                    }
+                }
+                uint32_t acc_w = 0;
+                for (int j = 0; j < n; ++j) {  // bp.hpp:277-298 and 312-318
+                    const uint32_t cb = col_ptr[j], ce = col_ptr[j + 1];
+                    double t = p.uniform_prior ? p.prior0 : prior[j];
+                    for (uint32_t q = cb; q < ce; ++q) {
+                        const size_t e = (size_t) csc2csr[q] * 32;
+                        if (active) st_msg(tile + e, t);
+                        t += active ? ld_msg(c2b + e) : 0.0;
+                    }
+                    if (LLR) {
+                        if (active) llr_tile[(size_t) j * 32] = t;
+                    }
+                    const uint32_t W = __ballot_sync(0xffffffffu, active && (t <= 0));
+                    if (lane == (j & 31)) acc_w = W;
+                    if ((j & 31) == 31 || j == n - 1) dec_w[(j & ~31) + lane] = acc_w;
+                    double u = 0;
+                    for (uint32_t q = ce; q-- > cb;) {
+                        const size_t e = (size_t) csc2csr[q] * 32;
+                        if (active) st_msg(tile + e, ld_msg(tile + e) + u);
+                        u += active ? ld_msg(c2b + e) : 0.0;
+                    }
+                }
+            } else {
+                for (int oi = 0; oi < p.order_len; ++oi) {  // bp.hpp:484-534, one bit after the other
+                    const uint32_t j = p.order[oi];
+                    if (j == 0xffffffffu) continue;
+                    const uint32_t cb = col_ptr[j], ce = col_ptr[j + 1];
+                    double L = p.uniform_prior ? p.prior0 : prior[j];
+                    for (uint32_t q = cb; q < ce; ++q) {
+                        const uint32_t e = csc2csr[q], i = row_idx[q];
+                        const uint32_t rb = row_ptr[i], re = row_ptr[i + 1];
+                        const uint32_t s = (syn_w[i] >> lane) & 1u;
+                        double c;
+                        if (METHOD == kMinimumSum) {
+                            uint32_t sg = s;
+                            double temp = DBL_MAX;
+                            for (uint32_t f = rb; f < re; ++f) {
+                                if (f == e) continue;
+                                const double b = active ? ld_msg(tile + (size_t) f * 32) : 0.0;
+                                const double a = fabs(b);
+                                if (a < temp) temp = a;
+                                if (b <= 0) sg += 1;
+                            }
+                            c = ((sg & 1u) ? -alpha : alpha) * temp;
+                        } else {
+                            double x = 1.0;
+                            for (uint32_t f = rb; f < re; ++f) {
+                                if (f == e) continue;
+                                x *= ps_tanh_half(active ? ld_msg(tile + (size_t) f * 32) : 0.0);
+                            }
+                            c = (s ? -1.0 : 1.0) * ps_atanh2(x);
+                        }
+                        if (active) {
+                            st_msg(c2b + (size_t) e * 32, c);
+                            st_msg(tile + (size_t) e * 32, L);
+                        }
+                        L += c;
+                    }
+                    if (LLR) {
+                        if (active) llr_tile[(size_t) j * 32] = L;
+                    }
+                    const uint32_t W = __ballot_sync(0xffffffffu, active && (L <= 0));
+                    if (lane == 0) dec_w[j] = W;
+                    double u = 0;
+                    for (uint32_t q = ce; q-- > cb;) {
+                        const size_t e = (size_t) csc2csr[q] * 32;
+                        if (active) st_msg(tile + e, ld_msg(tile + e) + u);
+                        u += active ? ld_msg(c2b + e) : 0.0;
+                    }
+                }
+            }
+        } else
         if (SCHED == kParallel) {
             // ---------------- check -> bit (bp.hpp:201-273), in place --------------------------------
             constexpr int RB = RowsPerBatch<DC, UNI>::v;
@@ -441,8 +563,8 @@ StreamKernel pick_stream_bucket(int dc, int dv, bool regular, bool llr) {
     if (dc <= 8 && dv <= 16) { BPB_PICK(8, 16, false); }
     if (dc <= 32 && dv <= 4) { BPB_PICK(32, 4, false); }
     if (dc <= 32 && dv <= 16) { BPB_PICK(32, 16, false); }
+    BPB_PICK(0, 0, false);  // any degree: the two-array scheme of the reference
 #undef BPB_PICK
-    return nullptr;
 }
 
 }  // namespace bpb

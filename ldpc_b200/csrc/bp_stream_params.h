@@ -45,6 +45,7 @@ using StreamKernel = void (*)(const StreamParams);
 #endif
 template <int DC, int DV, bool UNI> struct SerialBatch { static constexpr int v = UNI ? BPB_SERIAL_SB_UNI : ((DC <= 8 && DV <= 4) ? 2 : 1); };
 inline int serial_batch(int dc, int dv, bool regular) {
+    if (dc > 32 || dv > 16) return 1;  // generic kernel: plain order
     if (regular && dc == 6 && dv == 3) return SerialBatch<6, 3, true>::v;
     if (dc <= 8 && dv <= 4) return SerialBatch<8, 4, false>::v;
     return 1;

@@ -96,14 +96,3 @@ def test_v1_vs_v2_same_logical_error_rate():
     out2 = MonteCarloBscSimulation(H, error_rate=0.20, Decoder=bpd_v1, target_run_count=1000, seed=42).run()
     assert out1["logical_error_rate"] == out2["logical_error_rate"]
     assert 0 < out1["fail_count"] < 1000
-
-
-def test_unsupported_degree_fails_loudly():
-    dense = np.zeros((3, 60), np.uint8)
-    dense[0, :40] = 1  # a check of degree 40 > 32
-    dense[1, 30:] = 1
-    dense[2, ::2] = 1
-    d = BpDecoder(dense, error_rate=0.05, max_iter=3, bp_method="ms", input_vector_type="syndrome")
-    with pytest.raises(Exception) as e:
-        d.decode_batch(np.ones((4, 3), np.uint8))
-    assert "degree" in str(e.value)

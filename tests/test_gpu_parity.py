@@ -174,3 +174,23 @@ def test_golden_fixtures_from_reference(kernel):
         got = _decode_gpu(H, z["syndromes"], z["channel"], kernel=kernel, **kw)
         assert_same_decode(got, (z["decoding"], z["converged"], z["iters"], z["llr"]),
                            llr_exact=(str(z["bp_method"]) == "ms"))
+
+
+def test_large_degrees_generic_path(port_oracle):
+    """Row degree 40 / column degree 20 exceed the register-array buckets: the streaming family falls back to the
+    reference's own two-array, two-sweep scheme (any degree).  All four method x schedule combinations."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(33)
+    m, n = 24, 90
+    dense = (rng.random((m, n)) < 0.25).astype(np.uint8)
+    dense[0, :40] = 1
+    dense[:20, 7] = 1
+    H = sp.csr_matrix(dense)
+    assert H.sum(1).max() >= 40 and H.sum(0).max() >= 20
+    err = (rng.random((400, n)) < 0.03).astype(np.uint8)
+    syn = codes.syndromes_of(H, err)
+    for method, sched in (("ms", "parallel"), ("ps", "parallel"), ("ms", "serial"), ("ps", "serial")):
+        kw = dict(max_iter=8, bp_method=method, schedule=sched, ms_scaling_factor=0.8)
+        want = port_oracle.decode_batch(H, syn, 0.03, **kw)
+        got = _decode_gpu(H, syn, 0.03, **kw)
+        assert_same_decode(got, want, llr_exact=(method == "ms"))
