@@ -34,7 +34,11 @@ template <int DV, bool UNI> struct ColsPerBatch { static constexpr int v = UNI ?
 // Parallel schedule: two 256-thread CTAs per SM (<= 128 registers) measured best (0.87 vs 0.77 of HBM peak with one
 // CTA of 168 registers); the serial schedule keeps the registers for its larger load batches.
 template <int METHOD, int SCHED, int DC, int DV, bool LLR, bool UNI>
-__global__ void __launch_bounds__(256, (SCHED == kParallel && DC <= 8 && DV <= 4) ? 2 : 1) bp_stream_kernel(const StreamParams p) {
+#ifndef BPB_SERIAL_MINBLOCKS
+#define BPB_SERIAL_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParallel ? 2 : BPB_SERIAL_MINBLOCKS) : 1)
+    bp_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;

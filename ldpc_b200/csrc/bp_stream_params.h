@@ -41,7 +41,7 @@ using StreamKernel = void (*)(const StreamParams);
 
 // Bits of one level the serial-schedule kernel keeps in flight together (host pads the schedule to this).
 #ifndef BPB_SERIAL_SB_UNI
-#define BPB_SERIAL_SB_UNI 4
+#define BPB_SERIAL_SB_UNI 2  // measured: 2 bits x 16 warps/SM beats 4 bits x 8 warps/SM by 6 % at n = 10^4
 #endif
 template <int DC, int DV, bool UNI> struct SerialBatch { static constexpr int v = UNI ? BPB_SERIAL_SB_UNI : ((DC <= 8 && DV <= 4) ? 2 : 1); };
 inline int serial_batch(int dc, int dv, bool regular) {
