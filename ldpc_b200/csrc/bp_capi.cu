@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -338,6 +339,13 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     const int want = serial ? std::max(32, (int) align_up((uint32_t) std::max(pl.mean_level, 1), 32))
                             : std::max(32, (int) align_up((uint32_t) std::max(g.m, (g.n + 1) / 2), 32));
     T = std::min(T, std::min(want, serial ? 128 : 256));
+    if (const char *ov = std::getenv("BPB_SMEM_GROUP_THREADS")) {  // tuning override: threads per group
+        const int t_ov = std::atoi(ov);
+        if (t_ov >= 32 && t_ov % 32 == 0 && t_ov <= maxt) {
+            T = t_ov;
+            G = std::min(G, maxt / T);
+        }
+    }
     const int block = G * T;
     const size_t smem_bytes = tab + (size_t) G * pl.group_bytes;
     BPB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes));
