@@ -1,23 +1,14 @@
-# 2-GPU check of the bench contract (torchrun, NCCL only for the timing barrier)
+# N-GPU check of the bench contract (torchrun, NCCL only for the timing barrier).  Usage: bash scripts/gpu_multi.sh N
+N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-   bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
-   bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err
-timeout 600 python - <<'PY' > gpurun_out/multi_api.log 2>&1
-import sys, time, numpy as np
-sys.path.insert(0, ".")
-from ldpc_b200 import codes
-from ldpc_b200.parallel import MultiGpuBpDecoder
-from ldpc_b200 import BpDecoder
-H = codes.regular_ldpc(1000, 3, 6, seed=1)
-syn = codes.bsc_syndromes(H, 0.05, 1 << 18, seed=7)
-kw = dict(error_rate=0.05, max_iter=50, bp_method="ms", ms_scaling_factor=0.625, input_vector_type="syndrome")
-one = BpDecoder(H, device=0, **kw); ref = one.decode_batch(syn)
-multi = MultiGpuBpDecoder(H, devices=[0, 1], **kw)
-out = multi.decode_batch(syn)
-t = time.perf_counter(); out = multi.decode_batch(syn); dt = time.perf_counter() - t
-print("multi == single:", np.array_equal(out, ref), np.array_equal(multi.iter_batch, one.iter_batch), "decodes/s (pageable host arrays)", syn.shape[0] / dt)
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+   bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+   bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.json 2> gpurun_out/bench_ref_n$N.err
+python - <<PY
+import json
+d = json.load(open("gpurun_out/bench_n$N.json"))
+print("N=%d value %.4e ms/step %.2f e2e %.4e stream_family %.4e frac %.3f" % (d["n_gpus"], d["value"], d["ms_per_step"], d["e2e"]["value"], d["stream_family"]["value"], d["stream_family"]["roofline"]["frac"]))
+r = json.load(open("gpurun_out/bench_ref_n$N.json")); print("reference arm %.4e" % r["value"], r["cpu_baseline"]["cores"])
 PY
-cat gpurun_out/bench_n2.json | cut -c1-400; tail -3 gpurun_out/bench_n2.err; cat gpurun_out/bench_ref_n2.json | cut -c1-300; tail -2 gpurun_out/bench_ref_n2.err; cat gpurun_out/multi_api.log | tail -3
+tail -2 gpurun_out/bench_n$N.err
