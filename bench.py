@@ -184,10 +184,12 @@ def run_ours(args, rank, local_rank, world):
         raise RuntimeError("bench.py needs a CUDA device (ldpc_b200 has no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # keep stdout to the ONE JSON line: native libraries (NCCL's version banner, ...) write to fd 1 directly, so park
+    # the real stdout and point fd 1 at stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner to stdout when NCCL_DEBUG asks for it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     H = build_code()
     m, n = H.shape
@@ -370,7 +372,8 @@ def run_ours(args, rank, local_rank, world):
                 "gpu_launches": int(launches), "cpu_baseline": cpu_baseline}
         if stream_family is not None:
             line["stream_family"] = stream_family
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
