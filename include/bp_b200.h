@@ -72,7 +72,8 @@ int bpb_set_kernel(bpb_decoder *h, int kernel_family);                          
  *
  * bpb_decode_batch takes HOST pointers (pageable or pinned) and includes the H2D/D2H copies.
  * bpb_decode_batch_device takes DEVICE pointers on the handle's device and enqueues everything on
- * `cuda_stream` (a cudaStream_t passed as void*, NULL = default stream) without synchronising. */
+ * `cuda_stream` (a cudaStream_t passed as void*, NULL = default stream) without synchronising; d_decoding must be
+ * 4-byte aligned and d_log_prob_ratios 8-byte aligned (any cudaMalloc / framework allocation is). */
 int bpb_decode_batch(bpb_decoder *h, int input_type, const uint8_t *input, int64_t batch, uint8_t *decoding,
                      uint8_t *converged, int32_t *iterations, double *log_prob_ratios);
 int bpb_decode_batch_device(bpb_decoder *h, int input_type, const uint8_t *d_input, int64_t batch,

@@ -194,3 +194,21 @@ def test_large_degrees_generic_path(port_oracle):
         want = port_oracle.decode_batch(H, syn, 0.03, **kw)
         got = _decode_gpu(H, syn, 0.03, **kw)
         assert_same_decode(got, want, llr_exact=(method == "ms"))
+
+
+def test_bposd_surface_many_failures(port_oracle):
+    """BP+OSD-0 where BP fails most of the time (rotated surface code, product-sum): every non-converged row goes
+    through the device-side compaction and the host elimination; compare with the oracle's BP + OSD-0 restatement."""
+    H = codes.rotated_surface_code_x(7)
+    syn = codes.bsc_syndromes(H, 0.08, 5000, seed=17)
+    kw = dict(max_iter=12, bp_method="ps", schedule="parallel")
+    d = BpOsdDecoder(H, error_rate=0.08, osd_method="osd0", **kw)
+    got = d.decode_batch(syn)
+    bp = port_oracle.decode_batch(H, syn, 0.08, **kw)
+    want = bp[0].copy()
+    bad = ~bp[1]
+    assert bad.mean() > 0.3
+    want[bad] = port_oracle.osd0_batch(H, syn[bad], bp[3][bad])
+    assert np.array_equal(d.converge_batch, bp[1]) and np.array_equal(d.iter_batch, bp[2])
+    assert np.array_equal(got, want)
+    assert np.array_equal(codes.syndromes_of(H, got), syn)
