@@ -1,0 +1,109 @@
+"""One native decoder handle (``bpb_decoder*`` of include/bp_b200.h).
+
+Calls go through the Cython binding ``_bp_shim`` (the reference's kind of host shim, built by
+``ldpc_b200/csrc/build_shim.py`` / ``__graft_entry__.build()``) and fall back to the ``ctypes`` binding of the SAME
+library when the extension has not been built.  Both are bindings of the CUDA library; neither decodes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+try:  # the compiled Cython shim
+    from . import _bp_shim
+except ImportError:  # pragma: no cover - depends on the build
+    _bp_shim = None
+
+BINDING = "cython" if _bp_shim is not None else "ctypes"
+
+
+class Handle:
+    def __init__(self, m: int, n: int, rows: np.ndarray, cols: np.ndarray, device: int):
+        self.m, self.n = m, n
+        self._nh = None
+        self._ct = None
+        if _bp_shim is not None:
+            _capi.lib()  # raises a clear ImportError if libbp_b200.so itself is missing
+            try:
+                self._nh = _bp_shim.NativeHandle(m, n, rows, cols, device)
+            except _bp_shim.NativeError as e:
+                raise _capi.BpbError(str(e)) from None
+            self.ptr = C.c_void_p(self._nh.ptr)
+        else:
+            L = _capi.lib()
+            h = C.c_void_p()
+            rc = L.bpb_create(m, n, rows.size, rows.ctypes.data_as(_capi._i32p), cols.ctypes.data_as(_capi._i32p),
+                              device, C.byref(h))
+            if rc != _capi.OK:
+                msg = L.bpb_last_error(None)
+                raise _capi.BpbError(f"bpb_create failed ({rc}): {msg.decode() if msg else ''}")
+            self._ct = h
+            self.ptr = h
+
+    def close(self):
+        if self._ct is not None:
+            _capi.lib().bpb_destroy(self._ct)
+            self._ct = None
+        self._nh = None  # NativeHandle.__dealloc__ destroys the decoder
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _wrap(self, fn, *args):
+        try:
+            return fn(*args)
+        except _bp_shim.NativeError as e:
+            raise _capi.BpbError(str(e)) from None
+
+    def configure(self, channel, max_iter, method, schedule, ms_scaling, order, kernel):
+        ch = np.ascontiguousarray(channel, dtype=np.float64)
+        od = np.ascontiguousarray(order, dtype=np.int32)
+        if self._nh is not None:
+            self._wrap(self._nh.set_channel, ch)
+            self._wrap(self._nh.set_params, int(max_iter), int(method), int(schedule), float(ms_scaling), od, int(kernel))
+            return
+        L, h = _capi.lib(), self._ct
+        _capi.check(h, L.bpb_set_channel(h, ch.ctypes.data_as(_capi._f64p), self.n))
+        _capi.check(h, L.bpb_set_max_iter(h, int(max_iter)))
+        _capi.check(h, L.bpb_set_method(h, int(method)))
+        _capi.check(h, L.bpb_set_schedule(h, int(schedule)))
+        _capi.check(h, L.bpb_set_ms_scaling_factor(h, float(ms_scaling)))
+        _capi.check(h, L.bpb_set_serial_schedule_order(h, od.ctypes.data_as(_capi._i32p), od.size))
+        _capi.check(h, L.bpb_set_kernel(h, int(kernel)))
+
+    def decode_batch(self, input_type, inputs, dec, conv, its, llr):
+        if self._nh is not None:
+            return self._wrap(self._nh.decode_batch, int(input_type), inputs, dec, conv, its, llr)
+        h = self._ct
+        rc = _capi.lib().bpb_decode_batch(h, input_type, _capi.host_ptr(inputs), inputs.shape[0], _capi.host_ptr(dec),
+                                          _capi.host_ptr(conv), _capi.host_ptr(its), _capi.host_ptr(llr))
+        _capi.check(h, rc)
+
+    def bposd_decode_batch(self, syn, dec, conv, its, threads):
+        if self._nh is not None:
+            return self._wrap(self._nh.bposd_decode_batch, syn, dec, conv, its, int(threads))
+        h = self._ct
+        rc = _capi.lib().bpb_bposd_decode_batch(h, _capi.host_ptr(syn), syn.shape[0], _capi.host_ptr(dec),
+                                                _capi.host_ptr(conv), _capi.host_ptr(its), None, int(threads))
+        _capi.check(h, rc)
+
+    def osd0_host(self, syn, llr, conv, dec, threads):
+        if self._nh is not None:
+            return self._wrap(self._nh.osd0_host, syn, llr, conv, dec, int(threads))
+        h = self._ct
+        rc = _capi.lib().bpb_osd0_host(h, _capi.host_ptr(syn), _capi.host_ptr(llr), _capi.host_ptr(conv), syn.shape[0],
+                                       _capi.host_ptr(dec), int(threads))
+        _capi.check(h, rc)
+
+    def info(self) -> dict:
+        if self._nh is not None:
+            return self._wrap(self._nh.info)
+        inf = _capi.BpbInfo()
+        _capi.check(self._ct, _capi.lib().bpb_get_info(self._ct, C.byref(inf)))
+        return {k: getattr(inf, k) for k, _ in inf._fields_}

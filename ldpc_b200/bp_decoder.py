@@ -21,6 +21,7 @@ import numpy as np
 import scipy.sparse
 
 from . import _capi
+from ._native import Handle
 from .helpers import convert_to_binary_sparse
 
 
@@ -60,6 +61,7 @@ class BpDecoderBase:
         self._device = int(kwargs.get("device", 0))
         self._kernel = kwargs.get("kernel", "auto")
 
+        self._native = None  # the bpb_decoder handle (Cython binding, or ctypes when the extension is not built)
         self._handle = None
         self._dirty = True
         self.m, self.n, self._rows, self._cols = _coo_of(pcm)
@@ -101,48 +103,27 @@ class BpDecoderBase:
             list of floats of length equal to the block length of the code {self.n}.")
 
     # ------------------------------------------------------------------ C-ABI plumbing
-    def __del__(self):
-        try:
-            if getattr(self, "_handle", None):
-                _capi.lib().bpb_destroy(self._handle)
-                self._handle = None
-        except Exception:
-            pass
-
     def _ensure_handle(self):
-        L = _capi.lib()
-        if self._handle is None:
-            h = C.c_void_p()
-            rc = L.bpb_create(self.m, self.n, self._rows.size, self._rows.ctypes.data_as(_capi._i32p),
-                              self._cols.ctypes.data_as(_capi._i32p), self._device, C.byref(h))
-            if rc != _capi.OK:
-                msg = L.bpb_last_error(None)
-                raise _capi.BpbError(f"bpb_create failed ({rc}): {msg.decode() if msg else ''}")
-            self._handle = h
+        """Create / refresh the native decoder; returns the raw ``bpb_decoder*`` (ctypes.c_void_p)."""
+        if self._native is None:
+            self._native = Handle(self.m, self.n, self._rows, self._cols, self._device)
+            self._handle = self._native.ptr
             self._dirty = True
         if self._dirty:
             if self._schedule == _capi.SERIAL_RELATIVE:
                 raise NotImplementedError("schedule='serial_relative' is not implemented on the GPU path")
             if self._random_serial_schedule:
                 raise NotImplementedError("random_serial_schedule is not implemented on the GPU path")
-            h = self._handle
-            ch = np.ascontiguousarray(self._channel, dtype=np.float64)
-            _capi.check(h, L.bpb_set_channel(h, ch.ctypes.data_as(_capi._f64p), self.n))
-            _capi.check(h, L.bpb_set_max_iter(h, int(self._max_iter)))
-            _capi.check(h, L.bpb_set_method(h, int(self._bp_method)))
-            _capi.check(h, L.bpb_set_schedule(h, int(self._schedule)))
-            _capi.check(h, L.bpb_set_ms_scaling_factor(h, float(self._ms_scaling_factor)))
-            order = np.ascontiguousarray(self._serial_schedule_order, dtype=np.int32)
-            _capi.check(h, L.bpb_set_serial_schedule_order(h, order.ctypes.data_as(_capi._i32p), order.size))
             kern = {"auto": _capi.KERNEL_AUTO, "stream": _capi.KERNEL_STREAM, "smem": _capi.KERNEL_SMEM}[
                 str(self._kernel).lower()]
-            _capi.check(h, L.bpb_set_kernel(h, kern))
+            self._native.configure(self._channel, self._max_iter, self._bp_method, self._schedule,
+                                   self._ms_scaling_factor, self._serial_schedule_order, kern)
             self._dirty = False
         return self._handle
 
     def _decode_device_batch(self, inputs: np.ndarray, input_type: int, want_llr: bool):
         """inputs: contiguous uint8 [B, m|n].  Returns (decoding u8 [B,n], converged bool[B], iters i32[B], llr|None)."""
-        h = self._ensure_handle()
+        self._ensure_handle()
         B = inputs.shape[0]
         big = B * self.n >= (1 << 20)  # large results land in pinned memory (asynchronous D2H at full PCIe speed)
         alloc = _capi.pinned_empty if big else np.empty
@@ -150,17 +131,13 @@ class BpDecoderBase:
         conv = alloc((B,), dtype=np.uint8)
         its = alloc((B,), dtype=np.int32)
         llr = alloc((B, self.n), dtype=np.float64) if want_llr else None
-        rc = _capi.lib().bpb_decode_batch(h, input_type, _capi.host_ptr(inputs), B, _capi.host_ptr(dec),
-                                          _capi.host_ptr(conv), _capi.host_ptr(its), _capi.host_ptr(llr))
-        _capi.check(h, rc)
+        self._native.decode_batch(input_type, inputs, dec, conv, its, llr)
         return dec, conv.astype(bool), its, llr
 
     def info(self) -> dict:
         """Introspection of the native handle (kernel family, launch shape, launches so far)."""
-        h = self._ensure_handle()
-        inf = _capi.BpbInfo()
-        _capi.check(h, _capi.lib().bpb_get_info(h, C.byref(inf)))
-        return {k: getattr(inf, k) for k, _ in inf._fields_}
+        self._ensure_handle()
+        return self._native.info()
 
     # ------------------------------------------------------------------ properties (reference :167-579)
     @property

@@ -81,11 +81,10 @@ class BpOsdDecoder(BpDecoderBase):
             return
         if self._osd_order != 0:
             raise NotImplementedError("only OSD-0 (osd_order == 0) is implemented; OSD_E / OSD_CS are out of scope")
-        h = self._ensure_handle()
+        self._ensure_handle()
         conv = np.ascontiguousarray(converged, dtype=np.uint8)
-        rc = _capi.lib().bpb_osd0_host(h, _capi.host_ptr(syndromes), _capi.host_ptr(llr), _capi.host_ptr(conv),
-                                       syndromes.shape[0], _capi.host_ptr(decoding), self._osd_threads)
-        _capi.check(h, rc)
+        self._native.osd0_host(syndromes, np.ascontiguousarray(llr, dtype=np.float64), conv, decoding,
+                               self._osd_threads)
 
     # ------------------------------------------------------------------ decode (:78-136)
     def decode(self, syndrome: np.ndarray) -> np.ndarray:
@@ -119,7 +118,7 @@ class BpOsdDecoder(BpDecoderBase):
             return np.zeros((0, self.n), dtype=dtype)
         if self._osd_method != OSD_OFF and self._osd_order != 0:
             raise NotImplementedError("only OSD-0 (osd_order == 0) is implemented; OSD_E / OSD_CS are out of scope")
-        h = self._ensure_handle()
+        self._ensure_handle()
         B = vec.shape[0]
         dec = np.empty((B, self.n), dtype=np.uint8)
         conv = np.empty(B, dtype=np.uint8)
@@ -128,9 +127,7 @@ class BpOsdDecoder(BpDecoderBase):
             d, c, i, _ = self._decode_device_batch(vec, _capi.INPUT_SYNDROME, want_llr=False)
             dec, conv, its = d, c.astype(np.uint8), i
         else:
-            rc = _capi.lib().bpb_bposd_decode_batch(h, _capi.host_ptr(vec), B, _capi.host_ptr(dec), _capi.host_ptr(conv),
-                                                    _capi.host_ptr(its), None, self._osd_threads)
-            _capi.check(h, rc)
+            self._native.bposd_decode_batch(vec, dec, conv, its, self._osd_threads)
         self.converge_batch, self.iter_batch, self.log_prob_ratios_batch = conv.astype(bool), its, None
         return dec if dtype == np.uint8 else dec.astype(dtype)
 

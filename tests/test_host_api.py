@@ -27,6 +27,24 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in lib.bpb_version()
 
 
+def test_cython_shim_is_the_binding():
+    """The host side is a Cython shim over the C-ABI (like the reference's); ctypes only binds the same library when
+    the extension has not been built."""
+    from ldpc_b200 import _native
+    if _native.BINDING != "cython":
+        pytest.skip("ldpc_b200/_bp_shim not built (run __graft_entry__.build())")
+    from ldpc_b200 import _bp_shim
+    rows = np.array([0, 0, 1, 1], np.int32)
+    cols = np.array([0, 1, 1, 2], np.int32)
+    h = _bp_shim.NativeHandle(2, 3, rows, cols, -1)  # host-only handle
+    h.set_channel(np.full(3, 0.1))
+    inf = h.info()
+    assert inf["m"] == 2 and inf["n"] == 3 and inf["nnz"] == 4 and inf["smem_family_available"] == 1
+    with pytest.raises(_bp_shim.NativeError):
+        h.decode_batch(0, np.ones((1, 2), np.uint8), np.zeros((1, 3), np.uint8), np.zeros(1, np.uint8),
+                       np.zeros(1, np.int32), None)
+
+
 def test_no_cpu_fallback_without_gpu():
     """On a box without a GPU, creating a decoder must fail loudly (never silently decode on the CPU)."""
     import torch
