@@ -212,3 +212,19 @@ def test_bposd_surface_many_failures(port_oracle):
     assert np.array_equal(d.converge_batch, bp[1]) and np.array_equal(d.iter_batch, bp[2])
     assert np.array_equal(got, want)
     assert np.array_equal(codes.syndromes_of(H, got), syn)
+
+
+@pytest.mark.parametrize("schedule", ["parallel", "serial"])
+def test_large_code_n10000(port_oracle, schedule):
+    """BASELINE config 5's code (n = 10^4 (3,6)-LDPC): the messages of one syndrome (240 kB) do not fit in shared
+    memory, so only the streaming family can run it, with the graph tables and syndrome words in global memory."""
+    H = codes.regular_ldpc(10000, 3, 6, seed=1)
+    syn = np.concatenate([codes.bsc_syndromes(H, 0.05, 40, seed=7), codes.bsc_syndromes(H, 0.08, 8, seed=8)])
+    kw = dict(max_iter=40, bp_method="ms", schedule=schedule, ms_scaling_factor=0.625)
+    want = port_oracle.decode_batch(H, syn, 0.05, **kw)
+    d = BpDecoder(H, error_rate=0.05, input_vector_type="syndrome", **kw)
+    got = d.decode_batch(syn, return_llr=True)
+    assert_same_decode((got, d.converge_batch, d.iter_batch, d.log_prob_ratios_batch), want, llr_exact=True)
+    assert d.info()["kernel_family"] == 1 and not want[1].all()
+    with pytest.raises(Exception):
+        BpDecoder(H, error_rate=0.05, kernel="smem", **kw).decode_batch(syn[:2])
