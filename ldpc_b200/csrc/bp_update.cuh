@@ -18,30 +18,33 @@ __device__ __forceinline__ void check_node_update(const double (&b)[DC], int deg
         // The reference builds |c_k| = min_{k' != k} |b_k'| from a prefix and a suffix running minimum with
         // strict '<' updates starting at DBL_MAX (bp.hpp:237-268).  min is exact and order-free, NaNs never
         // win a '<', so the same value is min2 for the argmin edge and min1 for every other edge.
+        // The same two running minima as the reference (bp.hpp:237-268): a forward one and a backward one, both
+        // seeded with DBL_MAX and updated on strict '<' (a NaN or +inf magnitude never replaces the running value),
+        // |c_k| = min(prefix_k, suffix_k).  Slots beyond the degree hold DBL_MAX, the neutral element.
         uint32_t tsgn = s;  // total_sgn, bp.hpp:236-242
-        double min1 = DBL_MAX, min2 = DBL_MAX;
-        int arg = -1;
+        double a[DC], pre[DC];
+        bool neg[DC];
 #pragma unroll
         for (int k = 0; k < DC; ++k) {
-            if (k < deg) {
-                if (b[k] <= 0) tsgn += 1;
-                const double a = fabs(b[k]);
-                if (a < min1) {
-                    min2 = min1;
-                    min1 = a;
-                    arg = k;
-                } else if (a < min2) {
-                    min2 = a;
-                }
-            }
+            neg[k] = (k < deg) && (b[k] <= 0);
+            tsgn += neg[k] ? 1u : 0u;
+            a[k] = (k < deg) ? fabs(b[k]) : DBL_MAX;
         }
+        double run = DBL_MAX;
 #pragma unroll
         for (int k = 0; k < DC; ++k) {
+            pre[k] = run;
+            run = (a[k] < run) ? a[k] : run;
+        }
+        run = DBL_MAX;
+#pragma unroll
+        for (int k = DC - 1; k >= 0; --k) {
             if (k < deg) {
-                const double mag = (k == arg) ? min2 : min1;
-                const uint32_t sg = tsgn + ((b[k] <= 0) ? 1u : 0u);  // bp.hpp:252-260
-                c[k] = mag * ((sg & 1u) ? -alpha : alpha);           // bp.hpp:262
+                const double mag = (run < pre[k]) ? run : pre[k];    // bp.hpp:256-258
+                const uint32_t sg = tsgn + (neg[k] ? 1u : 0u);        // bp.hpp:252-260
+                c[k] = mag * ((sg & 1u) ? -alpha : alpha);            // bp.hpp:262
             }
+            run = (a[k] < run) ? a[k] : run;
         }
     } else {
         // bp.hpp:205-218: c_k = (prod_{k'<k} t_k') * (prod_{k'>k} t_k'), products accumulated left-to-right
