@@ -16,7 +16,7 @@
 // message comes from two ELL tables, row_pos[k*M + i] (k-th edge of row i, ascending column = the reference's
 // iterate_row order) and col_pos[k*N + j] (k-th edge of column j, ascending row).  The host chooses the positions by
 // 16-colouring the edges of the (row half-warp, slot) x (column half-warp, slot) incidence graph (Koenig), colour
-// = shared-memory bank pair, so that both passes are free of bank conflicts (bp_capi.cu, build_smem_plan).
+// = shared-memory bank pair, so that both passes are free of bank conflicts (bp_plan.cpp, build_smem_plan).
 // Hard decisions are ballot words (one bit per column).  The candidate syndrome (bp.hpp:290-300) is accumulated the
 // way the reference does it, from the columns: a bit decided 1 XORs its checks into a word array preset to the
 // syndrome (shared-memory atomicXor; only ~p*n bits are 1), and an OR-reduction barrier tests it for zero.

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParalle
             // The reference updates the bits one after another.  Two bits that share no check touch disjoint
             // messages (bit j reads the b2c of the OTHER edges of its checks and writes its own edges), so they
             // commute; the host sorts the schedule into levels (level(j) > level of every earlier bit that shares a
-            // check with j, bp_capi.cu: build_serial_batches) and hands the kernel batches of SB bits of one level.
+            // check with j, bp_plan.cpp: build_serial_batches) and hands the kernel batches of SB bits of one level.
             // All loads of a batch are issued before any of its stores, which multiplies the transactions in
             // flight per warp by SB; the result is the reference's, bit for bit.
             constexpr int SB = SerialBatch<DC, DV, UNI>::v;
