@@ -1,26 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- syndrome decodes/sec of the batched BP decoder on BASELINE.json's headline configuration.
+"""bench.py -- syndrome decodes/sec of the batched BP decoder on the BASELINE.json configurations.
 
-Workload (BASELINE.json configs[1], the one the metric is quoted on): (3,6)-regular LDPC, n=1000, m=500,
-min-sum, parallel schedule, max_iter=50, ms_scaling_factor=0.625, one batch of 2^20 synthetic BSC(p=0.05)
-syndromes per step.  A "step" = one pass of the hot path over that batch.
+    python bench.py [--config 1..5] [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--batch B] [--kernel auto|stream|smem|edge]
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--kernel auto|stream|smem]
+Default = BASELINE.json configs[1], the one the metric is quoted on: (3,6)-regular LDPC n=1000, min-sum, parallel
+schedule, max_iter=50, ms_scaling_factor=0.625, one batch of 2^20 synthetic BSC(p=0.05) syndromes per step.  A "step"
+is one pass of the hot path over that batch.  `--config 3/4/5` run the other BASELINE configurations through the
+same code and print the same JSON shape (config 1 is the reference's README case, CPU-sized; it runs too).
 
-* ours      : `value` = decodes/s with the syndromes already resident in HBM (CUDA events on the launching
-              stream, max over ranks); `e2e` = the same through the host-buffer C-ABI call (pinned host memory,
-              H2D + kernels + D2H inside the timed region); `roofline` for the message-update kernel against the
-              measured HBM peak (MEASURED_PEAKS.json); `cpu_baseline` = the reference's own C++ timed on this box.
+* ours      : `value` = decodes/s with the syndromes already resident in HBM (CUDA events on the launching stream,
+              max over ranks); `e2e` = the same through the host-buffer C-ABI call (pinned host memory, H2D + kernels
+              + D2H inside the timed region); `e2e_python` = the same through the Python class from pageable numpy;
+              `roofline` = the dominant kernel against ITS ceiling (on-chip family: shared-memory bandwidth; streaming
+              family: measured HBM bandwidth, MEASURED_PEAKS.json); `roofline_hbm` = the HBM-resident (streaming)
+              family on the same batch; `cpu_baseline` = the reference's own C++ timed on this box's host cores,
+              its outputs compared bit for bit with the GPU's (`parity_checked`).
 * reference : the unmodified reference C++ (oracle/_ref) on all host threads, on a bounded sample of the same
-              workload per step.
+              workload per step.  This arm imports no product code.
 
 N > 1 is launched by torchrun (one rank per GPU); the batch shards by rank with no collective on the data path
-("weak" scaling: every rank decodes its own 2^20 syndromes), only the timing is reduced (max over ranks).
+("weak" scaling: every rank decodes its own batch), only the timing is reduced (max over ranks).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import importlib.util
 import json
 import os
 import subprocess
@@ -33,14 +39,56 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_CODE, DV, DC, CODE_SEED = 1000, 3, 6, 1
-P_ERR, MAX_ITER, MS_SCALING = 0.05, 50, 0.625
-METRIC = "syndrome decodes/sec (50 BP iters) on n=1000 (3,6)-LDPC"
+
+def _codes():
+    """ldpc_b200/codes.py loaded by path (pure numpy/scipy): the reference arm must not import the product package
+    (its __init__ loads the native libraries)."""
+    if "ldpc_b200" in sys.modules:
+        from ldpc_b200 import codes
+        return codes
+    spec = importlib.util.spec_from_file_location("_bench_codes", os.path.join(ROOT, "ldpc_b200", "codes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
-def workload_name(batch):
-    return (f"(3,6)-regular LDPC n={N_CODE} (seed {CODE_SEED}), min_sum parallel max_iter={MAX_ITER} "
-            f"ms_scaling={MS_SCALING}, batch={batch} BSC p={P_ERR} syndromes")
+# ------------------------------------------------------------------------------------------ workloads
+def config_table(idx):
+    """BASELINE.json configs.  Returns a dict: code builder, decoder keywords, batch, p."""
+    c = _codes()
+    if idx == 1:
+        return dict(idx=1, label="hamming_code(5) 5x31, product_sum parallel max_iter=2, uniform random syndromes",
+                    H=lambda: c.hamming_code(5), p=0.1, syndromes="uniform", batch=1 << 20, osd=False,
+                    kw=dict(max_iter=2, bp_method="ps", schedule="parallel", ms_scaling_factor=1.0),
+                    metric="syndrome decodes/sec (2 BP iters, product_sum) on hamming_code(5)")
+    if idx == 2:
+        return dict(idx=2, label="(3,6)-regular LDPC n=1000 (seed 1), min_sum parallel max_iter=50 ms_scaling=0.625",
+                    H=lambda: c.regular_ldpc(1000, 3, 6, seed=1), p=0.05, syndromes="bsc", batch=1 << 20, osd=False,
+                    kw=dict(max_iter=50, bp_method="ms", schedule="parallel", ms_scaling_factor=0.625),
+                    metric="syndrome decodes/sec (50 BP iters) on n=1000 (3,6)-LDPC")
+    if idx == 3:
+        return dict(idx=3, label="d=13 rotated surface code X checks 84x169, product_sum parallel max_iter=30",
+                    H=lambda: c.rotated_surface_code_x(13), p=0.05, syndromes="bsc", batch=1000000, osd=False,
+                    also_osd=True, kw=dict(max_iter=30, bp_method="ps", schedule="parallel", ms_scaling_factor=1.0),
+                    metric="syndrome decodes/sec (30 BP iters, product_sum) on d=13 rotated surface code")
+    if idx == 4:
+        return dict(idx=4, label="[[144,12,12]] bivariate bicycle H_X 72x144, min_sum parallel max_iter=50 "
+                                 "ms_scaling=0.625 + OSD-0", H=lambda: c.bivariate_bicycle_144(), p=0.003,
+                    syndromes="bsc", batch=1000000, osd=True,
+                    kw=dict(max_iter=50, bp_method="ms", schedule="parallel", ms_scaling_factor=0.625),
+                    metric="syndrome decodes/sec (BP+OSD-0) on [[144,12,12]] bivariate bicycle code")
+    if idx == 5:
+        return dict(idx=5, label="(3,6)-regular LDPC n=10000 (seed 1), min_sum SERIAL max_iter=100 ms_scaling=0.625",
+                    H=lambda: c.regular_ldpc(10000, 3, 6, seed=1), p=0.05, syndromes="bsc", batch=1 << 18, osd=False,
+                    sweep=(0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08),
+                    kw=dict(max_iter=100, bp_method="ms", schedule="serial", ms_scaling_factor=0.625),
+                    metric="syndrome decodes/sec (100 serial BP iters) on n=10000 (3,6)-LDPC")
+    raise SystemExit("--config must be 1..5")
+
+
+def workload_name(cfg, batch):
+    src = f"BSC p={cfg['p']}" if cfg["syndromes"] == "bsc" else "uniform random"
+    return f"config {cfg['idx']}: {cfg['label']}, batch={batch} {src} syndromes"
 
 
 def measured_peak():
@@ -77,7 +125,6 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def mark(self):
-        """Number of samples received so far (to cut the window of interest out of the stream)."""
         return len(self.rows)
 
     def stop(self, first=0):
@@ -125,60 +172,122 @@ def host_cores():
     return max(1, n)
 
 
-def build_code():
-    from ldpc_b200 import codes
-    return codes.regular_ldpc(N_CODE, DV, DC, seed=CODE_SEED)
+def host_syndromes(cfg, H, count, seed=7):
+    c = _codes()
+    if cfg["syndromes"] == "uniform":
+        return np.random.default_rng(seed).integers(0, 2, size=(count, H.shape[0])).astype(np.uint8)
+    return c.bsc_syndromes(H, cfg["p"], count, seed=seed)
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank, world):
+def reference_decoder(cfg, H):
+    """(callable(syndromes) -> (outputs..., seconds), kind, cores): the reference's own CPU implementation."""
+    import oracle
+    kw = dict(cfg["kw"])
+    if oracle.have_ref():
+        ref, cores = oracle.RefOracle(), host_cores()
+
+        def run(syn, want_llr=False):
+            return ref.decode_batch(H, syn, cfg["p"], want_llr=want_llr, osd_method=1 if cfg["osd"] else 0,
+                                    threads=cores, return_seconds=True, **kw)
+        return run, "reference", cores
+    if not oracle.have_port():
+        oracle.build()
+    port = oracle.PortOracle()
+
+    def run(syn, want_llr=False):
+        t0 = time.perf_counter()
+        r = port.decode_batch(H, syn, cfg["p"], want_llr=(want_llr or cfg["osd"]), **kw)
+        dec = r[0]
+        if cfg["osd"] and (~r[1]).any():
+            dec = dec.copy()
+            dec[~r[1]] = port.osd0_batch(H, syn[~r[1]], r[3][~r[1]])
+        return dec, r[1], r[2], r[3], time.perf_counter() - t0
+    return run, "port", 1
+
+
+def sized_sample(run, syn_probe, total, target_s):
+    """Number of syndromes the reference arm decodes in about `target_s` seconds (probe run on `syn_probe`)."""
+    dt = run(syn_probe)[-1]
+    rate = syn_probe.shape[0] / max(dt, 1e-6)
+    return int(max(syn_probe.shape[0], min(total, rate * target_s))), rate
+
+
+def run_reference(args, cfg, rank, world):
     """The reference's own CPU implementation (unmodified C++ in oracle/_ref, else the C port) on host cores."""
     if rank != 0:
         return
-    import oracle
-    from ldpc_b200 import codes
-    H = build_code()
-    if oracle.have_ref():
-        impl, kind = oracle.RefOracle(), "reference"
-        cores = host_cores()
-    else:
-        if not oracle.have_port():
-            oracle.build()
-        impl, kind, cores = oracle.PortOracle(), "port", 1
-    # bounded sample per step: ~2-4 s of CPU work at ~4-5k decodes/s/core
-    sample = int(min(args.batch, max(2048, 4096 * cores)))
-    syn = codes.bsc_syndromes(H, P_ERR, sample, seed=7)
-    kw = dict(max_iter=MAX_ITER, bp_method="ms", schedule="parallel", ms_scaling_factor=MS_SCALING, want_llr=False)
-
-    def step():
-        t0 = time.perf_counter()
-        if kind == "reference":
-            impl.decode_batch(H, syn, P_ERR, threads=cores, **kw)
-        else:
-            impl.decode_batch(H, syn, P_ERR, **kw)
-        return time.perf_counter() - t0
-
-    for _ in range(args.warmup):
-        step()
-    t = sum(step() for _ in range(args.steps))
+    H = cfg["H"]()
+    run, kind, cores = reference_decoder(cfg, H)
+    B = int(args.batch)
+    probe = host_syndromes(cfg, H, int(min(B, 64 * cores)))
+    # bounded sample per step: about 3 s of CPU work
+    sample, _ = sized_sample(run, probe, B, 3.0)
+    syn = host_syndromes(cfg, H, sample)
+    for _ in range(min(args.warmup, 1)):
+        run(syn)
+    t = sum(run(syn)[-1] for _ in range(args.steps))
     value = sample * args.steps / t
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "decodes/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": "decodes/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.batch), "sample_per_step": sample},
+            "config": {"workload": workload_name(cfg, B), "sample_per_step": sample},
             "cpu_baseline": {"value": value, "unit": "decodes/s", "cores": cores, "kind": kind,
                              "sample": f"{sample} syndromes of the workload per step, {cores} threads, one decoder "
-                                       f"object per thread (reference C++ BpDecoder::decode per syndrome)"},
+                                       f"object per thread (reference C++ BpDecoder::decode"
+                                       f"{' + OsdDecoder::decode' if cfg['osd'] else ''} per syndrome)"},
             "e2e": {"value": value, "unit": "decodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def run_ours(args, rank, local_rank, world):
+def device_syndromes(torch, cfg, H, B, dev, seed):
+    """Synthetic syndromes generated on the device (seeded per rank): e ~ Bernoulli(p), s = H e mod 2."""
+    m, n = H.shape
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    d_syn = torch.empty((B, m), dtype=torch.uint8, device=dev)
+    if cfg["syndromes"] == "uniform":
+        d_syn.copy_(torch.randint(0, 2, (B, m), device=dev, generator=gen, dtype=torch.uint8))
+        return d_syn
+    Hd = torch.tensor(H.toarray(), dtype=torch.float16, device=dev)
+    chunk = max(1, min(1 << 16, (1 << 28) // max(n, 1)))
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        e = (torch.rand((hi - lo, n), device=dev, generator=gen) < cfg["p"]).to(torch.float16)
+        d_syn[lo:hi] = (e @ Hd.T).to(torch.int32).remainder_(2).to(torch.uint8)
+    return d_syn
+
+
+def roofline_record(info, alg_bytes, kms, clocks, E, n, m, its_sum, B, conv_frac):
+    """The dominant kernel against ITS ceiling.  Streaming family: algorithmic HBM bytes over the measured HBM copy
+    bandwidth.  On-chip / edge family: the same message bytes move through SHARED memory instead,
+    so the ceiling is the shared-memory crossbar, 128 B/clk/SM (B300_MICROARCH.md, LDS/STS) x SMs x SM clock."""
+    fam = info["kernel_family"]
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    common = {"achieved": achieved, "unit": "GB/s", "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+              "mean_iterations": its_sum / B, "converged_fraction": conv_frac}
+    if fam == 1:
+        peak, src = measured_peak()
+        return {"bound": "hbm", "peak": peak, "frac": achieved / peak, "traffic": None, "peak_source": src,
+                "kernel": "bp_stream_kernel", "handed_to_second_stage": int(info["stream_handed_off"]), **common}
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    sms = info["sm_count"] or 148
+    peak = 128.0 * sms * sm_mhz * 1e6 / 1e9
+    return {"bound": "smem", "peak": peak, "frac": achieved / peak, "traffic": None,
+            "peak_source": f"derived: 128 B/clk/SM shared-memory crossbar x {sms} SMs x {sm_mhz:.0f} MHz (SM clock "
+                           f"sampled during the run); message bytes 4*E*8 per iteration move through shared memory, "
+                           f"not HBM",
+            "kernel": {2: "bp_smem_kernel", 3: "bp_edge_kernel"}.get(fam, "?"),
+            "note": "on-chip family: index-table and decision-bit accesses share the same crossbar (about +30 % "
+                    "wavefronts) and the kernel is co-limited by instruction issue (profiles/)", **common}
+
+
+def run_ours(args, cfg, rank, local_rank, world):
     import torch
     import torch.distributed as dist
-    from ldpc_b200 import BpDecoder, _capi
+    from ldpc_b200 import BpDecoder, BpOsdDecoder, _capi
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (ldpc_b200 has no CPU path)")
@@ -191,28 +300,19 @@ def run_ours(args, rank, local_rank, world):
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    H = build_code()
+    H = cfg["H"]()
     m, n = H.shape
     E = int(H.nnz)
     B = int(args.batch)
+    kw = dict(cfg["kw"])
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    d_syn = device_syndromes(torch, cfg, H, B, dev, 1234 + rank)
 
-    # synthetic BSC syndromes generated on the device (seeded per rank): e ~ Bernoulli(p), s = H e mod 2
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    Hd = torch.tensor(H.toarray(), dtype=torch.float16, device=dev)
-    d_syn = torch.empty((B, m), dtype=torch.uint8, device=dev)
-    chunk = 1 << 16
-    for lo in range(0, B, chunk):
-        hi = min(B, lo + chunk)
-        e = (torch.rand((hi - lo, n), device=dev, generator=gen) < P_ERR).to(torch.float16)
-        d_syn[lo:hi] = (e @ Hd.T).to(torch.int32).remainder_(2).to(torch.uint8)
-    del Hd
-
-    dec = BpDecoder(H, error_rate=P_ERR, max_iter=MAX_ITER, bp_method="ms", ms_scaling_factor=MS_SCALING,
-                    schedule="parallel", input_vector_type="syndrome", device=local_rank, kernel=args.kernel)
+    cls = BpOsdDecoder if cfg["osd"] else BpDecoder
+    extra = dict(osd_method="osd0") if cfg["osd"] else dict(input_vector_type="syndrome")
+    dec = cls(H, error_rate=cfg["p"], device=local_rank, kernel=args.kernel, **extra, **kw)
     h = dec._ensure_handle()
     L = _capi.lib()
     d_dec = torch.empty((B, n), dtype=torch.uint8, device=dev)
@@ -220,11 +320,20 @@ def run_ours(args, rank, local_rank, world):
     d_its = torch.empty(B, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    def device_step():
-        rc = L.bpb_decode_batch_device(h, _capi.INPUT_SYNDROME, C.c_void_p(d_syn.data_ptr()), B,
+    def bp_step(handle):
+        rc = L.bpb_decode_batch_device(handle, _capi.INPUT_SYNDROME, C.c_void_p(d_syn.data_ptr()), B,
                                        C.c_void_p(d_dec.data_ptr()), C.c_void_p(d_conv.data_ptr()),
                                        C.c_void_p(d_its.data_ptr()), None, C.c_void_p(stream.cuda_stream))
-        _capi.check(h, rc)
+        _capi.check(handle, rc)
+
+    def bposd_step(handle):
+        rc = L.bpb_bposd_decode_batch_device(handle, C.c_void_p(d_syn.data_ptr()), B, C.c_void_p(d_dec.data_ptr()),
+                                             C.c_void_p(d_conv.data_ptr()), C.c_void_p(d_its.data_ptr()), None,
+                                             C.c_void_p(stream.cuda_stream))
+        _capi.check(handle, rc)
+
+    dev_osd = cfg["osd"] and hasattr(L, "bpb_bposd_decode_batch_device")
+    device_step = (lambda: bposd_step(h)) if dev_osd else (lambda: bp_step(h))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -240,8 +349,6 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     # ---- device-resident throughput ------------------------------------------------------------------
-    # (the nvidia-smi sampler was started before the data generation: it needs ~1 s to deliver its first sample;
-    #  the reported clocks are the samples taken from the first warm-up step to the end of the timed steps)
     warm = max(args.warmup, 3)
     first_sample = sampler.mark()
     for _ in range(warm):
@@ -249,84 +356,69 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     launches0 = dec.info()["launches"]
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kernel_ms = []
     ev[0].record(stream)
     for k in range(args.steps):
         device_step()
         ev[k + 1].record(stream)
     barrier()
     clocks = sampler.stop(first_sample) if rank == 0 else None
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms.append(dec.info()["last_kernel_ms"])
-    launches = dec.info()["launches"] - launches0
-    total_ms = max_over_ranks(total_ms)
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+    info = dec.info()
+    kms = float(info["last_kernel_ms"])
+    launches = info["launches"] - launches0
     value = B * world * args.steps / (total_ms * 1e-3)
 
-    # statistics of the decoded batch (same every step: same inputs)
     its_sum = int(d_its.sum(dtype=torch.int64).item())
     conv_frac = float(d_conv.to(torch.float32).mean().item())
 
     # ---- roofline of the message-update kernel -----------------------------------------------------------
-    # algorithmic bytes: per iteration 4*E*w (check pass reads b2c + writes c2b, bit pass reads
-    # c2b + writes b2c; w = 8, binary64) + n + m; once per decode m + n + 4 + 1.
+    # algorithmic bytes, w = 8 (binary64): parallel schedule 4*E*w per iteration (check pass
+    # reads b2c + writes c2b, bit pass reads c2b + writes b2c), serial schedule sum_i d_i(d_i-1)*w + E*w; + n + m per
+    # iteration; once per decode m + n + 4 + 1.
     w = 8
-    info = dec.info()
-    alg_bytes = its_sum * (4 * E * w + n + m) + B * (m + n + 5)
+    serial = kw["schedule"] == "serial"
+    rdeg = np.diff(H.tocsr().indptr).astype(np.int64)
+    per_iter = (int((rdeg * (rdeg - 1)).sum()) * w + E * w if serial else 4 * E * w) + n + m
+    alg_bytes = its_sum * per_iter + B * (m + n + 5)
     if info["kernel_family"] == 1 and info["stream_iterations"] > 0:
-        # streaming family: count the iterations the timed kernel itself executed (its ramp-down hands the last
-        # stragglers to the second-stage kernel, whose time is not in kernel_ms)
-        alg_bytes = info["stream_iterations"] * (4 * E * w + n + m) + (B - info["stream_handed_off"]) * (m + n + 5)
-    kms = float(np.mean(kernel_ms))
-    peak, peak_src = measured_peak()
-    achieved = alg_bytes / (kms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "kernel": {1: "bp_stream_kernel", 2: "bp_smem_kernel"}.get(info["kernel_family"], "?"),
-                "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": ("on-chip family: messages stay in shared memory, so the algorithmic HBM bytes are never moved "
-                         "(frac > 1 by design; see roofline.traffic for the real DRAM bytes and DESIGN.md section 5.1)")
-                if info["kernel_family"] == 2 else "streaming family: messages resident in HBM",
-                "mean_iterations": its_sum / B, "converged_fraction": conv_frac,
-                "handed_to_second_stage": int(info["stream_handed_off"]) if info["kernel_family"] == 1 else 0}
+        # streaming family: count the iterations the timed kernel itself executed (its ramp-down may hand the last
+        # stragglers to a second-stage kernel, whose time is not in kernel_ms)
+        alg_bytes = info["stream_iterations"] * per_iter + (B - info["stream_handed_off"]) * (m + n + 5)
+    roofline = roofline_record(info, alg_bytes, kms, clocks, E, n, m, its_sum, B, conv_frac)
     traffic = load_traffic()
-    if roofline["kernel"] in traffic and traffic[roofline["kernel"]].get("batch") == B:
-        roofline["traffic"] = traffic[roofline["kernel"]]["dram_bytes_per_launch"]  # ncu --set full, per launch
+    tkey = roofline["kernel"] if cfg["idx"] == 2 else f"{roofline['kernel']}@config{cfg['idx']}"
+    if tkey in traffic and traffic[tkey].get("batch") == B:
+        roofline["traffic"] = traffic[tkey]["dram_bytes_per_launch"]  # one ncu --set full capture, per launch
+        roofline["traffic_source"] = traffic[tkey].get("source")
 
-    # ---- the streaming (HBM-resident) family on the same batch, for the record ----------------------------------
-    stream_family = None
-    if info["kernel_family"] == 2 and args.kernel == "auto" and not args.no_stream_family:
-        sdec = BpDecoder(H, error_rate=P_ERR, max_iter=MAX_ITER, bp_method="ms", ms_scaling_factor=MS_SCALING,
-                         schedule="parallel", input_vector_type="syndrome", device=local_rank, kernel="stream")
+    # ---- the HBM-resident (streaming) family on the same batch: first-class HBM roofline record -------------------
+    roofline_hbm = None
+    if info["kernel_family"] == 1:
+        roofline_hbm = dict(roofline, value=value, ms_per_step=total_ms / args.steps)
+    elif args.kernel == "auto" and not args.no_stream_family and not cfg["osd"]:
+        sdec = BpDecoder(H, error_rate=cfg["p"], input_vector_type="syndrome", device=local_rank, kernel="stream", **kw)
         sh = sdec._ensure_handle()
-
-        def stream_step():
-            rc = L.bpb_decode_batch_device(sh, _capi.INPUT_SYNDROME, C.c_void_p(d_syn.data_ptr()), B,
-                                           C.c_void_p(d_dec.data_ptr()), C.c_void_p(d_conv.data_ptr()),
-                                           C.c_void_p(d_its.data_ptr()), None, C.c_void_p(stream.cuda_stream))
-            _capi.check(sh, rc)
-
         for _ in range(2):
-            stream_step()
+            bp_step(sh)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(2):
-            stream_step()
+            bp_step(sh)
         e1.record(stream)
         barrier()
         s_ms = max_over_ranks(e0.elapsed_time(e1)) / 2
         sinfo = sdec.info()
-        s_bytes = sinfo["stream_iterations"] * (4 * E * w + n + m) + (B - sinfo["stream_handed_off"]) * (m + n + 5)
-        s_ach = s_bytes / (sinfo["last_kernel_ms"] * 1e-3) / 1e9
-        stream_family = {"value": B * world / (s_ms * 1e-3), "unit": "decodes/s", "ms_per_step": s_ms,
-                         "roofline": {"bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s",
-                                      "frac": s_ach / peak, "kernel": "bp_stream_kernel",
-                                      "kernel_ms": sinfo["last_kernel_ms"], "algorithmic_bytes_per_launch": s_bytes,
-                                      "handed_to_second_stage": int(sinfo["stream_handed_off"]),
-                                      "traffic": (traffic.get("bp_stream_kernel", {}).get("dram_bytes_per_launch")
-                                                  if traffic.get("bp_stream_kernel", {}).get("batch") == B else None)},
-                         "note": "same batch decoded by the HBM-streaming kernel family (kernel='stream'): messages "
-                                 "laid out batch-minor in HBM, one lane per syndrome"}
+        s_bytes = sinfo["stream_iterations"] * per_iter + (B - sinfo["stream_handed_off"]) * (m + n + 5)
+        roofline_hbm = roofline_record(sinfo, s_bytes, float(sinfo["last_kernel_ms"]), clocks, E, n, m, its_sum, B,
+                                       conv_frac)
+        roofline_hbm.update(value=B * world / (s_ms * 1e-3), ms_per_step=s_ms,
+                            note="same batch decoded by the HBM-streaming kernel family (kernel='stream'): messages "
+                                 "laid out batch-minor in HBM, one lane per syndrome")
+        if "bp_stream_kernel" in traffic and traffic["bp_stream_kernel"].get("batch") == B and cfg["idx"] == 2:
+            roofline_hbm["traffic"] = traffic["bp_stream_kernel"]["dram_bytes_per_launch"]
+            roofline_hbm["traffic_source"] = traffic["bp_stream_kernel"].get("source")
+        bp_step(h)  # leave d_dec / d_its / d_conv as the measured handle produced them
         del sdec
 
     # ---- end to end through the host-buffer API (pinned host memory, copies inside the timed region) --------
@@ -338,9 +430,13 @@ def run_ours(args, rank, local_rank, world):
     pin_in.array[...] = d_syn.cpu().numpy()
 
     def host_step():
-        rc = L.bpb_decode_batch(h, _capi.INPUT_SYNDROME, _capi.host_ptr(pin_in.array), B,
-                                _capi.host_ptr(pin_dec.array), _capi.host_ptr(pin_conv.array),
-                                _capi.host_ptr(pin_its.array), None)
+        if cfg["osd"]:
+            rc = L.bpb_bposd_decode_batch(h, _capi.host_ptr(pin_in.array), B, _capi.host_ptr(pin_dec.array),
+                                          _capi.host_ptr(pin_conv.array), _capi.host_ptr(pin_its.array), None, 0)
+        else:
+            rc = L.bpb_decode_batch(h, _capi.INPUT_SYNDROME, _capi.host_ptr(pin_in.array), B,
+                                    _capi.host_ptr(pin_dec.array), _capi.host_ptr(pin_conv.array),
+                                    _capi.host_ptr(pin_its.array), None)
         _capi.check(h, rc)
 
     host_step()
@@ -351,57 +447,105 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = B * world * e2e_steps / e2e_s
-    same = bool(np.array_equal(pin_dec.array[:4096], d_dec[:4096].cpu().numpy()))
+    n_cmp = min(B, 1 << 16)
+    same = bool(np.array_equal(pin_dec.array[:n_cmp], d_dec[:n_cmp].cpu().numpy()))
 
-    # ---- reference C++ on this box's host cores, bounded sample (rank 0, N = 1 only) ------------------------
-    cpu_baseline = None
+    # ---- the same batch through the Python class from pageable numpy (the call a user of the package makes) ------
+    e2e_python = None
+    if not args.no_python_e2e:
+        syn_np = np.array(pin_in.array)  # pageable copy
+        dec.decode_batch(syn_np)
+        barrier()
+        t0 = time.perf_counter()
+        out = dec.decode_batch(syn_np)
+        py_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_python = {"value": B * world / py_s, "unit": "decodes/s", "seconds": py_s,
+                      "api": f"{cls.__name__}.decode_batch(pageable numpy [B,m] uint8)",
+                      "matches_device_run": bool(np.array_equal(out[:n_cmp], pin_dec.array[:n_cmp]))}
+        del syn_np, out
+
+    # ---- BP + OSD-0 on the same batch (config 3 names plain BP; its failures are what OSD-0 is for) -------------
+    e2e_bposd = None
+    if cfg.get("also_osd") and not args.no_python_e2e:
+        od = BpOsdDecoder(H, error_rate=cfg["p"], device=local_rank, osd_method="osd0", **kw)
+        oh = od._ensure_handle()
+        o_dec = _capi.PinnedArray((B, n), np.uint8)
+
+        def osd_step():
+            rc = L.bpb_bposd_decode_batch(oh, _capi.host_ptr(pin_in.array), B, _capi.host_ptr(o_dec.array),
+                                          _capi.host_ptr(pin_conv.array), _capi.host_ptr(pin_its.array), None, 0)
+            _capi.check(oh, rc)
+        osd_step()
+        t0 = time.perf_counter()
+        osd_step()
+        o_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_bposd = {"value": B * world / o_s, "unit": "decodes/s", "seconds": o_s,
+                     "api": "bpb_bposd_decode_batch (BP + OSD-0 for the non-converged rows), pinned host buffers",
+                     "non_converged_fraction": 1.0 - conv_frac, "osd": od.info().get("osd_location", "host")}
+        del od
+
+    # ---- reference C++ on this box's host cores, bounded sample of the SAME batch (rank 0, N = 1 only) ------------
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_leg(H, pin_in.array)
+        cpu_baseline, parity = cpu_baseline_leg(cfg, H, pin_in.array, pin_dec.array, pin_conv.array, pin_its.array)
+
+    # ---- config 5: error-rate sweep with syndromes generated and scored on the device ------------------------------
+    sweep = None
+    if cfg.get("sweep") and rank == 0 and hasattr(L, "bpb_mc_bsc"):
+        sweep = []
+        for p in cfg["sweep"]:
+            sd = BpDecoder(H, error_rate=float(p), input_vector_type="syndrome", device=local_rank, **kw)
+            runs = min(B, 1 << 16)
+            t0 = time.perf_counter()
+            r = sd.monte_carlo_bsc(runs, seed=17)
+            sweep.append({"p": p, "runs": runs, "seconds": time.perf_counter() - t0, **r})
+            del sd
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "decodes/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": cfg["metric"], "value": value, "unit": "decodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(B), "batch_per_gpu": B, "parallelism": f"batch-shard x{world}",
-                           "l2": "no flush needed: per-step working set (messages + I/O, several GB) >> 126 MB L2",
+                "config": {"workload": workload_name(cfg, B), "batch_per_gpu": B,
+                           "parallelism": f"batch-shard x{world}",
+                           "l2": "no flush needed: per-step working set (messages + I/O) >> 126 MB L2"
+                                 if B * (m + n) > (1 << 28) else "inputs+outputs per step %d MB" % (B * (m + n) >> 20),
                            "kernel_family": roofline["kernel"], "grid": info["grid"], "block": info["block"]},
                 "clocks": clocks, "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "decodes/s", "h2d_bytes_per_step": B * m * world,
                         "d2h_bytes_per_step": B * (n + 5) * world, "steps": e2e_steps,
                         "matches_device_run": same},
                 "gpu_launches": int(launches), "cpu_baseline": cpu_baseline}
-        if stream_family is not None:
-            line["stream_family"] = stream_family
+        if parity is not None:
+            line.update(parity)
+        for key, val in (("roofline_hbm", roofline_hbm), ("e2e_python", e2e_python), ("e2e_bposd", e2e_bposd),
+                         ("sweep", sweep)):
+            if val is not None:
+                line[key] = val
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline_leg(H, syn_host):
-    """Reference C++ (oracle/_ref) or the C port, on a bounded sample of the SAME syndromes (~10-20 s)."""
-    import oracle
-    cores = host_cores()
-    kw = dict(max_iter=MAX_ITER, bp_method="ms", schedule="parallel", ms_scaling_factor=MS_SCALING, want_llr=False)
-    if oracle.have_ref():
-        ref = oracle.RefOracle()
-        sample = int(min(syn_host.shape[0], 8192 * cores))
-        syn = np.ascontiguousarray(syn_host[:sample])
-        ref.decode_batch(H, syn[: 64 * cores], P_ERR, threads=cores, **kw)
-        dt = ref.decode_batch(H, syn, P_ERR, threads=cores, return_seconds=True, **kw)[-1]
-        return {"value": sample / dt, "unit": "decodes/s", "cores": cores, "kind": "reference",
-                "sample": f"first {sample} syndromes of the GPU batch, {cores} threads (cgroup cpu quota) x one reference "
-                          f"BpDecoder each, decode loop only"}
-    if not oracle.have_port():
-        oracle.build()
-    port = oracle.PortOracle()
-    sample = int(min(syn_host.shape[0], 32768))
+def cpu_baseline_leg(cfg, H, syn_host, gpu_dec, gpu_conv, gpu_its):
+    """Reference C++ (oracle/_ref) or the C port on a bounded sample of the SAME syndromes (10-20 s), and the bitwise
+    comparison of its outputs with what the GPU produced for those rows."""
+    run, kind, cores = reference_decoder(cfg, H)
+    B = syn_host.shape[0]
+    probe = np.ascontiguousarray(syn_host[: int(min(B, 64 * cores))])
+    sample, _ = sized_sample(run, probe, B, 12.0)
     syn = np.ascontiguousarray(syn_host[:sample])
-    t0 = time.perf_counter()
-    port.decode_batch(H, syn, P_ERR, **kw)
-    dt = time.perf_counter() - t0
-    return {"value": sample / dt, "unit": "decodes/s", "cores": 1, "kind": "port",
-            "sample": f"first {sample} syndromes of the GPU batch, single thread"}
+    out = run(syn)
+    dt = out[-1]
+    ok_dec = bool(np.array_equal(out[0], gpu_dec[:sample]))
+    ok_conv = bool(np.array_equal(np.asarray(out[1], bool), gpu_conv[:sample].astype(bool)))
+    ok_its = bool(np.array_equal(out[2], gpu_its[:sample]))
+    base = {"value": sample / dt, "unit": "decodes/s", "cores": cores, "kind": kind,
+            "sample": f"first {sample} syndromes of the GPU batch, {cores} threads x one reference decoder object each, "
+                      f"decode loop only"}
+    parity = {"parity_checked": sample, "parity_ok": ok_dec and ok_conv and ok_its,
+              "parity_detail": {"decoding": ok_dec, "converge": ok_conv, "iterations": ok_its, "checker": kind}}
+    return base, parity
 
 
 def main():
@@ -410,18 +554,23 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1 << 20)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "stream", "smem"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--batch", type=int, default=0, help="syndromes per GPU per step (default: the config's)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "stream", "smem", "edge"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream-family", action="store_true", help="skip the extra streaming-family measurement")
+    ap.add_argument("--no-python-e2e", action="store_true", help="skip the Python-API end-to-end measurements")
     args = ap.parse_args()
+    cfg = config_table(args.config)
+    if args.batch <= 0:
+        args.batch = cfg["batch"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank, world)
     else:
-        run_ours(args, rank, local_rank, world)
+        run_ours(args, cfg, rank, local_rank, world)
 
 
 if __name__ == "__main__":

@@ -39,7 +39,10 @@ enum { BPB_SERIAL = 0, BPB_PARALLEL = 1 };
 /* ldpc::bp::BpInputType, bp.hpp:34-38 */
 enum { BPB_INPUT_SYNDROME = 0, BPB_INPUT_RECEIVED_VECTOR = 1 };
 /* kernel family: AUTO picks the fastest family that supports the code */
-enum { BPB_KERNEL_AUTO = 0, BPB_KERNEL_STREAM = 1, BPB_KERNEL_SMEM = 2 };
+enum { BPB_KERNEL_AUTO = 0, BPB_KERNEL_STREAM = 1, BPB_KERNEL_SMEM = 2, BPB_KERNEL_EDGE = 3 };
+/* where OSD-0 runs in the BP+OSD entry points: AUTO = on the device when the code fits (m <= 1024 and the permuted
+ * bit matrix fits the shared memory of an SM), else on the host */
+enum { BPB_OSD_AUTO = 0, BPB_OSD_HOST = 1, BPB_OSD_DEVICE = 2 };
 
 /* --- life cycle ------------------------------------------------------------------------------
  * Replaces `new BpSparse(m,n,nnz)` + insert_entry per nonzero (_bp_decoder.pyx:9-49) and
@@ -61,6 +64,14 @@ int bpb_set_schedule(bpb_decoder *h, int schedule);                             
 int bpb_set_ms_scaling_factor(bpb_decoder *h, double ms_scaling_factor);         /* bp.hpp:62 */
 int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len); /* bp.hpp:69; NULL = 0..n-1 */
 int bpb_set_kernel(bpb_decoder *h, int kernel_family);                           /* new: BPB_KERNEL_* */
+int bpb_set_osd_location(bpb_decoder *h, int osd_location);                      /* new: BPB_OSD_* */
+/* new: split every HOST-pointer batch call of this handle over `count` CUDA devices.  One
+ * full decoder (own streams, pinned-speed staging, workspaces) is created per listed device (an ordinal may repeat);
+ * the host input array is split into `count` contiguous slices, one host thread per device drives its slice through
+ * the chunked H2D | kernels | D2H pipeline and the D2H copies land in disjoint ranges of the caller's output arrays:
+ * that is the whole "gather", no collective is involved.  Parameter setters called afterwards are forwarded.
+ * count == 0 (or ids == NULL) returns to the single device given at create time. */
+int bpb_set_devices(bpb_decoder *h, const int *device_ids, int count);
 
 /* --- decode: replaces BpDecoder::decode(vector<uint8_t>&) (bp.hpp:159-190) for a whole batch --
  * input  : [batch][m] (syndromes) or [batch][n] (received vectors), uint8 0/1, row-major
@@ -96,6 +107,25 @@ int bpb_osd0_host(bpb_decoder *h, const uint8_t *syndromes, const double *log_pr
 int bpb_bposd_decode_batch(bpb_decoder *h, const uint8_t *syndromes, int64_t batch, uint8_t *decoding,
                            uint8_t *converged, int32_t *iterations, uint8_t *bp_decoding, int threads);
 
+/* The same with DEVICE pointers, enqueued on `cuda_stream` without synchronising: BP, failure list, OSD-0 (the
+ * bit-packed elimination of osd_device.cu, osd.hpp:110-117) all on the device; nothing crosses PCIe.  Fails with
+ * BPB_ERR_UNSUPPORTED when the code does not fit the device OSD-0 kernel (see BPB_OSD_AUTO).  d_bp_decoding may be
+ * NULL. */
+int bpb_bposd_decode_batch_device(bpb_decoder *h, const uint8_t *d_syndromes, int64_t batch, uint8_t *d_decoding,
+                                  uint8_t *d_converged, int32_t *d_iterations, uint8_t *d_bp_decoding,
+                                  void *cuda_stream);
+
+/* --- Monte-Carlo runs on the binary symmetric channel without per-syndrome PCIe traffic: replaces the loop body of
+ * MonteCarloBscSimulation.run (src_python/ldpc/monte_carlo_simulation/mcs.py:124-139: generate_bsc_error ->
+ * H @ error % 2 -> Decoder.decode -> compare) for runs first_run .. first_run + runs - 1.  Run r flips bit j with
+ * probability flip_prob[j] (NULL: the decoder's channel probabilities) using Philox4x32-10 keyed by `seed` with
+ * counter (r, j / 4), so the drawn errors depend on (seed, r, j) only -- not on batch size, chunking or how the runs
+ * are sharded over devices.  with_osd != 0 adds OSD-0 for the BP failures (needs the device OSD-0 kernel).
+ * counts[0] = runs scored, [1] = runs whose decoding differs from the drawn error (the reference's fail_count),
+ * [2] = runs BP converged on, [3] = sum of BP iterations, [4] = runs that converged to a wrong decoding. */
+int bpb_mc_bsc(bpb_decoder *h, uint64_t seed, int64_t first_run, int64_t runs, const double *flip_prob, int with_osd,
+               int64_t counts[5]);
+
 /* --- introspection ----------------------------------------------------------------------------- */
 typedef struct {
     int m, n;
@@ -112,6 +142,11 @@ typedef struct {
     int smem_bytes_per_syndrome;  /* shared memory held per in-flight syndrome in that family */
     int64_t stream_iterations;    /* iterations executed by the last streaming-kernel launch (synchronises) */
     int64_t stream_handed_off;    /* syndromes its ramp-down handed to the second-stage kernel */
+    int osd_device_available;     /* 1 when OSD-0 for this code can run on the device */
+    int64_t osd_device_solved;    /* syndromes solved by the device OSD-0 kernel so far (host API calls only) */
+    int64_t osd_host_solved;      /* syndromes solved by the host elimination so far */
+    int64_t osd_host_inconsistent; /* of those (and of bpb_osd0_host calls): syndromes outside the image of H, for
+                                      which the result is defined here but differs from the reference's (osd_host.cpp) */
 } bpb_info;
 int bpb_get_info(const bpb_decoder *h, bpb_info *out);
 

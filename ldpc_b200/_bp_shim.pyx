@@ -9,7 +9,7 @@ the reference's ``decode`` never does.  The Python classes in bp_decoder.py / bp
 argument handling and call through this object; ``_capi.py`` (ctypes) binds the same library for callers without a
 compiled extension.
 """
-from libc.stdint cimport uint8_t, int32_t, int64_t, uintptr_t
+from libc.stdint cimport uint8_t, int32_t, int64_t, uint64_t, uintptr_t
 
 cdef extern from "bp_b200.h":
     ctypedef struct bpb_decoder:
@@ -33,6 +33,10 @@ cdef extern from "bp_b200.h":
         int smem_bytes_per_syndrome
         int64_t stream_iterations
         int64_t stream_handed_off
+        int osd_device_available
+        int64_t osd_device_solved
+        int64_t osd_host_solved
+        int64_t osd_host_inconsistent
     int bpb_create(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *cols, int device,
                    bpb_decoder **out) nogil
     void bpb_destroy(bpb_decoder *h) nogil
@@ -51,6 +55,10 @@ cdef extern from "bp_b200.h":
     int bpb_osd0_host(bpb_decoder *h, const uint8_t *syndromes, const double *llr, const uint8_t *converged,
                       int64_t batch, uint8_t *decoding, int threads) nogil
     int bpb_get_info(const bpb_decoder *h, bpb_info *out) nogil
+    int bpb_set_osd_location(bpb_decoder *h, int v) nogil
+    int bpb_set_devices(bpb_decoder *h, const int *ids, int count) nogil
+    int bpb_mc_bsc(bpb_decoder *h, uint64_t seed, int64_t first_run, int64_t runs, const double *flip_prob,
+                   int with_osd, int64_t *counts) nogil
 
 
 class NativeError(RuntimeError):
@@ -110,14 +118,35 @@ cdef class NativeHandle:
         self._check(rc)
 
     def bposd_decode_batch(self, const uint8_t[:, ::1] syn, uint8_t[:, ::1] dec, uint8_t[::1] conv, int32_t[::1] its,
-                           int threads):
+                           int threads, uint8_t[:, ::1] bp_dec=None):
         cdef int64_t B = syn.shape[0]
         cdef int rc
+        cdef uint8_t *bp = &bp_dec[0, 0] if bp_dec is not None else NULL
         if B == 0:
             return
         with nogil:
-            rc = bpb_bposd_decode_batch(self.h, &syn[0, 0], B, &dec[0, 0], &conv[0], &its[0], NULL, threads)
+            rc = bpb_bposd_decode_batch(self.h, &syn[0, 0], B, &dec[0, 0], &conv[0], &its[0], bp, threads)
         self._check(rc)
+
+    def set_osd_location(self, int v):
+        self._check(bpb_set_osd_location(self.h, v))
+
+    def set_devices(self, const int32_t[::1] ids):
+        cdef int k = <int> ids.shape[0]
+        cdef int rc
+        cdef const int *p = <const int *> &ids[0] if k else NULL
+        with nogil:
+            rc = bpb_set_devices(self.h, p, k)
+        self._check(rc)
+
+    def mc_bsc(self, uint64_t seed, int64_t first_run, int64_t runs, const double[::1] flip_prob, int with_osd):
+        cdef int64_t counts[5]
+        cdef int rc
+        cdef const double *fp = &flip_prob[0] if flip_prob is not None else NULL
+        with nogil:
+            rc = bpb_mc_bsc(self.h, seed, first_run, runs, fp, with_osd, counts)
+        self._check(rc)
+        return [counts[i] for i in range(5)]
 
     def osd0_host(self, const uint8_t[:, ::1] syn, const double[:, ::1] llr, const uint8_t[::1] conv,
                   uint8_t[:, ::1] dec, int threads):
@@ -139,4 +168,6 @@ cdef class NativeHandle:
                 "smem_family_available": inf.smem_family_available,
                 "smem_bank_multiplicity": inf.smem_bank_multiplicity,
                 "smem_bytes_per_syndrome": inf.smem_bytes_per_syndrome, "stream_iterations": inf.stream_iterations,
-                "stream_handed_off": inf.stream_handed_off}
+                "stream_handed_off": inf.stream_handed_off,
+                "osd_device_available": inf.osd_device_available, "osd_device_solved": inf.osd_device_solved,
+                "osd_host_solved": inf.osd_host_solved, "osd_host_inconsistent": inf.osd_host_inconsistent}

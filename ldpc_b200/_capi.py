@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -23,7 +24,8 @@ OK = 0
 PRODUCT_SUM, MINIMUM_SUM = 0, 1          # reference bp.hpp:23-26
 SERIAL, PARALLEL, SERIAL_RELATIVE = 0, 1, 2  # reference bp.hpp:28-32
 INPUT_SYNDROME, INPUT_RECEIVED_VECTOR, INPUT_AUTO = 0, 1, 2  # reference bp.hpp:34-38
-KERNEL_AUTO, KERNEL_STREAM, KERNEL_SMEM = 0, 1, 2
+KERNEL_AUTO, KERNEL_STREAM, KERNEL_SMEM, KERNEL_EDGE = 0, 1, 2, 3
+OSD_AUTO, OSD_HOST, OSD_DEVICE = 0, 1, 2
 
 
 class BpbInfo(C.Structure):
@@ -32,14 +34,16 @@ class BpbInfo(C.Structure):
                 ("grid", C.c_int), ("block", C.c_int), ("launches", C.c_int64), ("workspace_bytes", C.c_int64),
                 ("last_kernel_ms", C.c_double), ("smem_family_available", C.c_int),
                 ("smem_bank_multiplicity", C.c_int), ("smem_bytes_per_syndrome", C.c_int),
-                ("stream_iterations", C.c_int64), ("stream_handed_off", C.c_int64)]
+                ("stream_iterations", C.c_int64), ("stream_handed_off", C.c_int64),
+                ("osd_device_available", C.c_int), ("osd_device_solved", C.c_int64), ("osd_host_solved", C.c_int64), ("osd_host_inconsistent", C.c_int64)]
 
 
 EXPORTS = [
     "bpb_create", "bpb_destroy", "bpb_last_error", "bpb_set_channel", "bpb_set_max_iter", "bpb_set_method",
     "bpb_set_schedule", "bpb_set_ms_scaling_factor", "bpb_set_serial_schedule_order", "bpb_set_kernel",
     "bpb_decode_batch", "bpb_decode_batch_device", "bpb_osd0_host", "bpb_bposd_decode_batch", "bpb_get_info", "bpb_host_alloc",
-    "bpb_host_free", "bpb_version",
+    "bpb_host_free", "bpb_version", "bpb_set_osd_location", "bpb_set_devices", "bpb_bposd_decode_batch_device",
+    "bpb_mc_bsc",
 ]
 
 _lib = None
@@ -86,6 +90,14 @@ def lib():
     L.bpb_host_free.restype = None
     L.bpb_host_free.argtypes = [vp]
     L.bpb_version.restype = C.c_char_p
+    L.bpb_set_osd_location.restype = C.c_int
+    L.bpb_set_osd_location.argtypes = [vp, C.c_int]
+    L.bpb_set_devices.restype = C.c_int
+    L.bpb_set_devices.argtypes = [vp, _i32p, C.c_int]
+    L.bpb_bposd_decode_batch_device.restype = C.c_int
+    L.bpb_bposd_decode_batch_device.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp]
+    L.bpb_mc_bsc.restype = C.c_int
+    L.bpb_mc_bsc.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, _f64p, C.c_int, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -117,31 +129,47 @@ class _PinnedBlock:
             pass
 
 
-_POOL = {}            # nbytes -> [ptr, ...] free pinned blocks
+_POOL = {}            # bucket bytes (power of two) -> [ptr, ...] free pinned blocks
 _POOL_BYTES = [0]     # bytes currently allocated through the pool (free + in use)
-_POOL_LIMIT = int(os.environ.get("LDPC_B200_PINNED_LIMIT", str(8 << 30)))
+_POOL_FREE = [0]      # bytes sitting free in the pool
+_POOL_LIMIT = int(os.environ.get("LDPC_B200_PINNED_LIMIT", str(8 << 30)))   # allocated through the pool at most
+_POOL_CACHE = int(os.environ.get("LDPC_B200_PINNED_CACHE", str(4 << 30)))   # kept free for reuse at most
+_POOL_LOCK = threading.Lock()  # MultiGpuBpDecoder / user threads call decode_batch concurrently
 
 
 def _pool_give(ptr, nbytes):
-    _POOL.setdefault(nbytes, []).append(ptr)
+    with _POOL_LOCK:
+        if _POOL_FREE[0] + nbytes <= _POOL_CACHE:
+            _POOL.setdefault(nbytes, []).append(ptr)
+            _POOL_FREE[0] += nbytes
+            return
+        _POOL_BYTES[0] -= nbytes
+    lib().bpb_host_free(ptr)  # above the cache cap: really unpin
 
 
 def pinned_empty(shape, dtype):
-    """numpy array in page-locked host memory (full-speed, asynchronous PCIe copies), recycled through a small pool.
-    Falls back to ordinary memory when the pool limit is reached or pinning fails."""
+    """numpy array in page-locked host memory (full-speed, asynchronous PCIe copies), recycled through a small pool of
+    power-of-two sized blocks.  Falls back to ordinary memory when the pool limit is reached or pinning fails."""
     dtype = np.dtype(dtype)
     count = int(np.prod(shape))
-    nbytes = max(64, (count * dtype.itemsize + 4095) // 4096 * 4096)
-    free = _POOL.get(nbytes)
-    if free:
-        ptr = free.pop()
-    else:
-        if _POOL_BYTES[0] + nbytes > _POOL_LIMIT:
+    need = max(4096, count * dtype.itemsize)
+    nbytes = 1 << (need - 1).bit_length()
+    ptr = None
+    with _POOL_LOCK:
+        free = _POOL.get(nbytes)
+        if free:
+            ptr = free.pop()
+            _POOL_FREE[0] -= nbytes
+        elif _POOL_BYTES[0] + nbytes > _POOL_LIMIT:
             return np.empty(shape, dtype=dtype)
+        else:
+            _POOL_BYTES[0] += nbytes
+    if ptr is None:
         ptr = lib().bpb_host_alloc(nbytes)
         if not ptr:
+            with _POOL_LOCK:
+                _POOL_BYTES[0] -= nbytes
             return np.empty(shape, dtype=dtype)
-        _POOL_BYTES[0] += nbytes
     buf = (C.c_uint8 * nbytes).from_address(ptr)
     buf._owner = _PinnedBlock(ptr, nbytes)  # keeps the block out of the pool while any view of `buf` lives
     return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)

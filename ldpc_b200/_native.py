@@ -85,13 +85,35 @@ class Handle:
                                           _capi.host_ptr(conv), _capi.host_ptr(its), _capi.host_ptr(llr))
         _capi.check(h, rc)
 
-    def bposd_decode_batch(self, syn, dec, conv, its, threads):
+    def bposd_decode_batch(self, syn, dec, conv, its, threads, bp_dec=None):
         if self._nh is not None:
-            return self._wrap(self._nh.bposd_decode_batch, syn, dec, conv, its, int(threads))
+            return self._wrap(self._nh.bposd_decode_batch, syn, dec, conv, its, int(threads), bp_dec)
         h = self._ct
         rc = _capi.lib().bpb_bposd_decode_batch(h, _capi.host_ptr(syn), syn.shape[0], _capi.host_ptr(dec),
-                                                _capi.host_ptr(conv), _capi.host_ptr(its), None, int(threads))
+                                                _capi.host_ptr(conv), _capi.host_ptr(its), _capi.host_ptr(bp_dec),
+                                                int(threads))
         _capi.check(h, rc)
+
+    def set_osd_location(self, where: int):
+        if self._nh is not None:
+            return self._wrap(self._nh.set_osd_location, int(where))
+        _capi.check(self._ct, _capi.lib().bpb_set_osd_location(self._ct, int(where)))
+
+    def set_devices(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        if self._nh is not None:
+            return self._wrap(self._nh.set_devices, ids)
+        _capi.check(self._ct, _capi.lib().bpb_set_devices(self._ct, ids.ctypes.data_as(_capi._i32p), ids.size))
+
+    def mc_bsc(self, seed, first_run, runs, flip_prob, with_osd):
+        fp = None if flip_prob is None else np.ascontiguousarray(flip_prob, dtype=np.float64)
+        if self._nh is not None:
+            return self._wrap(self._nh.mc_bsc, int(seed), int(first_run), int(runs), fp, int(with_osd))
+        counts = (C.c_int64 * 5)()
+        rc = _capi.lib().bpb_mc_bsc(self._ct, int(seed), int(first_run), int(runs),
+                                    None if fp is None else fp.ctypes.data_as(_capi._f64p), int(with_osd), counts)
+        _capi.check(self._ct, rc)
+        return list(counts)
 
     def osd0_host(self, syn, llr, conv, dec, threads):
         if self._nh is not None:

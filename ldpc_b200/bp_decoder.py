@@ -58,8 +58,13 @@ class BpDecoderBase:
         random_schedule_seed = kwargs.get("random_schedule_seed", 0)
         serial_schedule_order = kwargs.get("serial_schedule_order", None)
         channel_probs = kwargs.get("channel_probs", [None])
-        self._device = int(kwargs.get("device", 0))
+        devices = kwargs.get("devices", None)
+        self._devices = None if devices is None else [int(d) for d in devices]
+        if self._devices is not None and len(self._devices) < 1:
+            raise ValueError("devices must name at least one CUDA device")
+        self._device = int(kwargs.get("device", self._devices[0] if self._devices else 0))
         self._kernel = kwargs.get("kernel", "auto")
+        self._osd_location = _capi.OSD_AUTO
 
         self._native = None  # the bpb_decoder handle (Cython binding, or ctypes when the extension is not built)
         self._handle = None
@@ -109,15 +114,20 @@ class BpDecoderBase:
             self._native = Handle(self.m, self.n, self._rows, self._cols, self._device)
             self._handle = self._native.ptr
             self._dirty = True
+            if self._devices is not None:
+                # one handle, one full decoder per device behind it (bpb_set_devices): host batches are split into
+                # contiguous slices, the D2H copies land in disjoint ranges of the output arrays
+                self._native.set_devices(self._devices)
         if self._dirty:
             if self._schedule == _capi.SERIAL_RELATIVE:
                 raise NotImplementedError("schedule='serial_relative' is not implemented on the GPU path")
             if self._random_serial_schedule:
                 raise NotImplementedError("random_serial_schedule is not implemented on the GPU path")
-            kern = {"auto": _capi.KERNEL_AUTO, "stream": _capi.KERNEL_STREAM, "smem": _capi.KERNEL_SMEM}[
-                str(self._kernel).lower()]
+            kern = {"auto": _capi.KERNEL_AUTO, "stream": _capi.KERNEL_STREAM, "smem": _capi.KERNEL_SMEM,
+                    "edge": _capi.KERNEL_EDGE}[str(self._kernel).lower()]
             self._native.configure(self._channel, self._max_iter, self._bp_method, self._schedule,
                                    self._ms_scaling_factor, self._serial_schedule_order, kern)
+            self._native.set_osd_location(self._osd_location)
             self._dirty = False
         return self._handle
 
@@ -133,6 +143,21 @@ class BpDecoderBase:
         llr = alloc((B, self.n), dtype=np.float64) if want_llr else None
         self._native.decode_batch(input_type, inputs, dec, conv, its, llr)
         return dec, conv.astype(bool), its, llr
+
+    def monte_carlo_bsc(self, runs: int, seed: int = 0, error_rate=None, first_run: int = 0,
+                        with_osd: bool = False) -> dict:
+        """``runs`` Monte-Carlo runs on the binary symmetric channel entirely on the device: errors drawn with
+        Philox4x32-10 (run r, bit j -> counter (r, j // 4), word j % 4, key = seed), syndromes ``H e``, decode,
+        compare ``decoding != error`` (the loop body of the reference's ``MonteCarloBscSimulation.run``,
+        mcs.py:124-139).  Only counters cross PCIe.  ``error_rate``: flip probability (scalar or per bit); default
+        is the decoder's own channel."""
+        self._ensure_handle()
+        fp = None
+        if error_rate is not None:
+            fp = np.ascontiguousarray(np.broadcast_to(np.asarray(error_rate, dtype=np.float64), (self.n,)))
+        c = self._native.mc_bsc(int(seed), int(first_run), int(runs), fp, 1 if with_osd else 0)
+        return {"run_count": int(c[0]), "fail_count": int(c[1]), "bp_converged": int(c[2]), "iter_sum": int(c[3]),
+                "converged_wrong": int(c[4])}
 
     def info(self) -> dict:
         """Introspection of the native handle (kernel family, launch shape, launches so far)."""
@@ -330,14 +355,14 @@ class BpDecoderBase:
         self._dirty = True
 
 
-_BP_KWARGS = ("channel_probs", "device", "kernel")
+_BP_KWARGS = ("channel_probs", "device", "devices", "kernel")
 
 
 class BpDecoder(BpDecoderBase):
     """Belief propagation decoder for binary linear codes (reference ``BpDecoder``, _bp_decoder.pyx:581-709).
 
-    Parameters are the reference's; ``device`` (CUDA ordinal) and ``kernel`` ('auto' | 'stream' | 'smem')
-    are additions.  ``decode`` takes one syndrome (or received vector); ``decode_batch`` takes ``[B, m]``.
+    Parameters are the reference's; ``device`` (CUDA ordinal), ``devices`` (list of ordinals: every batch call is split over
+    them inside the library) and ``kernel`` ('auto' | 'stream' | 'smem' | 'edge') are additions.  ``decode`` takes one syndrome (or received vector); ``decode_batch`` takes ``[B, m]``.
     """
 
     def __init__(self, pcm, error_rate: Optional[float] = None, error_channel=None, max_iter: Optional[int] = 0,

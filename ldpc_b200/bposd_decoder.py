@@ -1,4 +1,5 @@
-"""BpOsdDecoder: BP on the B200, OSD-0 on the host for the syndromes BP did not solve.
+"""BpOsdDecoder: BP on the B200, OSD-0 for the syndromes BP did not solve -- on the device too when the code fits the
+bit-packed elimination kernel (``osd_location='auto'``), else on the host.
 
 Mirrors ``ldpc.bposd_decoder.BpOsdDecoder`` (reference src_python/ldpc/bposd_decoder/_bposd_decoder.pyx:8-299):
 same constructor keywords and aliases, ``decode`` = zero shortcut -> BP -> (if not converged) OSD
@@ -25,13 +26,18 @@ class BpOsdDecoder(BpDecoderBase):
                  osd_method: Union[str, int, float] = 0, osd_order: int = 0, input_vector_type: str = "syndrome",
                  **kwargs):
         for key in kwargs.keys():
-            if key not in _BP_KWARGS + ("osd_threads", "random_serial_schedule"):
+            if key not in _BP_KWARGS + ("osd_threads", "random_serial_schedule", "osd_location"):
                 raise ValueError(f"Unknown parameter '{key}' passed to the BpDecoder constructor.")
         self._osd_threads = int(kwargs.pop("osd_threads", 0))
+        osd_location = str(kwargs.pop("osd_location", "auto")).lower()
+        if osd_location not in ("auto", "host", "device"):
+            raise ValueError("osd_location must be 'auto', 'host' or 'device'")
         super().__init__(pcm, error_rate=error_rate, error_channel=error_channel, max_iter=max_iter,
                          bp_method=bp_method, ms_scaling_factor=ms_scaling_factor, schedule=schedule,
                          omp_thread_count=omp_thread_count, random_schedule_seed=random_schedule_seed,
                          serial_schedule_order=serial_schedule_order, **kwargs)
+        self._osd_location = {"auto": _capi.OSD_AUTO, "host": _capi.OSD_HOST, "device": _capi.OSD_DEVICE}[osd_location]
+        self.bp_decoding_batch = None
         self._osd_method = OSD_OFF
         self._osd_order = 0
         self.osd_method = osd_method
@@ -107,8 +113,10 @@ class BpOsdDecoder(BpDecoderBase):
             self._osdw_decoding = dec[0].copy()
         return dec[0].astype(dtype)
 
-    def decode_batch(self, syndromes: np.ndarray) -> np.ndarray:
-        """Decode ``[B, m]`` syndromes: BP for all on the GPU, OSD-0 on the host for the non-converged rows."""
+    def decode_batch(self, syndromes: np.ndarray, return_bp_decoding: bool = False) -> np.ndarray:
+        """Decode ``[B, m]`` syndromes: BP for all on the GPU, then OSD-0 for the non-converged rows (on the device when
+        the code fits the elimination kernel, else on the host).  ``return_bp_decoding`` also keeps the raw BP output
+        in ``bp_decoding_batch``."""
         arr = np.asarray(syndromes)
         if arr.ndim != 2 or arr.shape[1] != self.m:
             raise ValueError(f"The syndromes must have shape [batch, {self.m}].")
@@ -120,14 +128,19 @@ class BpOsdDecoder(BpDecoderBase):
             raise NotImplementedError("only OSD-0 (osd_order == 0) is implemented; OSD_E / OSD_CS are out of scope")
         self._ensure_handle()
         B = vec.shape[0]
-        dec = np.empty((B, self.n), dtype=np.uint8)
-        conv = np.empty(B, dtype=np.uint8)
-        its = np.empty(B, dtype=np.int32)
+        big = B * self.n >= (1 << 20)
+        alloc = _capi.pinned_empty if big else np.empty
+        dec = alloc((B, self.n), dtype=np.uint8)
+        conv = alloc((B,), dtype=np.uint8)
+        its = alloc((B,), dtype=np.int32)
+        self.bp_decoding_batch = None
         if self._osd_method == OSD_OFF:
             d, c, i, _ = self._decode_device_batch(vec, _capi.INPUT_SYNDROME, want_llr=False)
             dec, conv, its = d, c.astype(np.uint8), i
         else:
-            self._native.bposd_decode_batch(vec, dec, conv, its, self._osd_threads)
+            bp = alloc((B, self.n), dtype=np.uint8) if return_bp_decoding else None
+            self._native.bposd_decode_batch(vec, dec, conv, its, self._osd_threads, bp)
+            self.bp_decoding_batch = bp
         self.converge_batch, self.iter_batch, self.log_prob_ratios_batch = conv.astype(bool), its, None
         return dec if dtype == np.uint8 else dec.astype(dtype)
 

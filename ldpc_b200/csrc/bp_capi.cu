@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 #include "bp_decoder.h"
 #include "bp_smem_params.h"
@@ -49,7 +50,9 @@ int ensure(bpb_decoder *h, bpb::DeviceBuffer &b, size_t bytes, bool zero = false
 std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
     return {&h->blob,     &h->order_d,   &h->counter,   &h->msg,        &h->dec_w,      &h->syn_w,    &h->llr_tile,
             &h->packed,   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
-            &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1]};
+            &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1],
+            &h->st_bp[0],   &h->st_bp[1],   &h->osd_conv,  &h->mc_thresh, &h->mc_err, &h->mc_syn, &h->mc_dec,
+            &h->mc_conv,    &h->mc_its,     &h->mc_counts};
 }
 
 void release(bpb::DeviceBuffer &b) {
@@ -129,10 +132,36 @@ __global__ void compact_failures_kernel(const uint8_t *__restrict__ conv, const 
     }
 }
 
+// BP+OSD on the device: the batch indices of the syndromes BP did not solve (order is irrelevant: every entry is
+// solved independently).  Optionally keeps a copy of the raw BP output rows for the caller.
+__global__ void list_failures_kernel(const uint8_t *__restrict__ conv, long long batch, unsigned long long *count,
+                                     unsigned long long *total, uint32_t *__restrict__ fail_idx) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    const long long rounds = (batch + stride - 1) / stride;
+    for (long long it = 0; it < rounds; ++it) {
+        const long long b = it * stride + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        const bool bad = b < batch && !conv[b];
+        const uint32_t mask = __ballot_sync(0xffffffffu, bad);
+        if (!mask) continue;
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(count, (unsigned long long) __popc(mask));
+            atomicAdd(total, (unsigned long long) __popc(mask));  // running total over the chunks of one host call
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (bad) fail_idx[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t) b;
+    }
+}
+
 // ---- graph blob ---------------------------------------------------------------------------------------
 
 int upload_graph(bpb_decoder *h) {
     const bpb::HostGraph &g = h->g;
+    // Kernels of an earlier bpb_decode_batch_device call (asynchronous on the caller's stream) may still be reading
+    // the tables rewritten below: drain the device first.  Only happens when the configuration changed.
+    BPB_CUDA(h, cudaDeviceSynchronize());
+    h->osd_plan = bpb::plan_osd_device(g, h->max_smem_optin);
     compute_priors(h);
     size_t words = (size_t) (g.m + 1) + (size_t) g.nnz + (size_t) (g.n + 1) + (size_t) g.nnz + (size_t) g.nnz;
     if (words & 1) words++;
@@ -178,7 +207,9 @@ int upload_graph(bpb_decoder *h) {
     }
     rc = ensure(h, h->order_d, upload.size() * sizeof(uint32_t));
     if (rc) return rc;
-    BPB_CUDA(h, cudaMemcpy(h->order_d.ptr, upload.data(), upload.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    BPB_CUDA(h, cudaMemcpyAsync(h->order_d.ptr, upload.data(), upload.size() * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, h->stream));
+    BPB_CUDA(h, cudaStreamSynchronize(h->stream));  // `upload` is pageable and dies at the end of this function
     build_smem_plan(h);
     if (h->smem_plan.ok) {
         rc = ensure(h, h->smem_tab, h->smem_plan.blob.size());
@@ -281,6 +312,7 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     p.out_llr = d_llr;
     p.order = (const uint32_t *) h->order_d.ptr;
     p.order_len = h->serial_entries;
+    p.llr_last_only = h->llr_last_only ? 1 : 0;
     BPB_CUDA(h, cudaEventRecord(h->kev0, st));
     k<<<grid, block, smem_bytes, st>>>(p);
     BPB_CUDA(h, cudaGetLastError());
@@ -395,6 +427,7 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.out_conv = d_conv;
     p.out_iters = d_iters;
     p.out_llr = d_llr;
+    p.llr_last_only = h->llr_last_only ? 1 : 0;
     if (!index_list) BPB_CUDA(h, cudaEventRecord(h->kev0, st));
     k<<<(int) grid64, block, smem_bytes, st>>>(p);
     BPB_CUDA(h, cudaGetLastError());
@@ -406,6 +439,13 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     h->last_block = block;
     return BPB_OK;
 }
+
+constexpr int kInputPacked = 16;  // internal input type: bit-packed syndromes already on the device
+int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, int64_t batch, uint8_t *d_decoding,
+                       uint8_t *d_converged, int32_t *d_iterations, double *d_llr, cudaStream_t cuda_stream);
+int multi_device_decode(bpb_decoder *h, int input_type, const uint8_t *input, int64_t batch, uint8_t *decoding,
+                        uint8_t *converged, int32_t *iterations, double *llr, uint8_t *bp_decoding, bool osd,
+                        int threads);
 
 int check_ready(bpb_decoder *h) {
     if (!h) return BPB_ERR_ARG;
@@ -489,6 +529,8 @@ int bpb_create(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *co
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&h->kev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->kev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **) &h->host_counts, 64, cudaHostAllocDefault);
     if (e != cudaSuccess) {
         std::string msg = std::string("CUDA init failed: ") + cudaGetErrorString(e);
         bpb_destroy(h);
@@ -500,6 +542,8 @@ int bpb_create(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *co
 
 void bpb_destroy(bpb_decoder *h) {
     if (!h) return;
+    for (bpb_decoder *c: h->children) bpb_destroy(c);
+    h->children.clear();
     if (h->device < 0) {
         delete h;
         return;
@@ -517,6 +561,10 @@ void bpb_destroy(bpb_decoder *h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->kev0) cudaEventDestroy(h->kev0);
     if (h->kev1) cudaEventDestroy(h->kev1);
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
+    for (int i = 0; i < 2; i++)
+        if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
+    if (h->host_counts) cudaFreeHost(h->host_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -529,6 +577,13 @@ int bpb_set_channel(bpb_decoder *h, const double *p, int n) {
     }
     h->channel.assign(p, p + n);
     h->graph_dirty = true;
+    for (bpb_decoder *c: h->children) {
+        const int rc_c = bpb_set_channel(c, p, n);
+        if (rc_c) {
+            h->err = c->err;
+            return rc_c;
+        }
+    }
     return BPB_OK;
 }
 
@@ -539,6 +594,13 @@ int bpb_set_max_iter(bpb_decoder *h, int v) {
         return BPB_ERR_ARG;
     }
     h->max_iter = v;
+    for (bpb_decoder *c: h->children) {
+        const int rc_c = bpb_set_max_iter(c, v);
+        if (rc_c) {
+            h->err = c->err;
+            return rc_c;
+        }
+    }
     return BPB_OK;
 }
 
@@ -549,6 +611,13 @@ int bpb_set_method(bpb_decoder *h, int v) {
         return BPB_ERR_ARG;
     }
     h->method = v;
+    for (bpb_decoder *c: h->children) {
+        const int rc_c = bpb_set_method(c, v);
+        if (rc_c) {
+            h->err = c->err;
+            return rc_c;
+        }
+    }
     return BPB_OK;
 }
 
@@ -560,12 +629,26 @@ int bpb_set_schedule(bpb_decoder *h, int v) {
     }
     if (h->schedule != v) h->graph_dirty = true;  // the shared-memory plan depends on the schedule
     h->schedule = v;
+    for (bpb_decoder *c: h->children) {
+        const int rc_c = bpb_set_schedule(c, v);
+        if (rc_c) {
+            h->err = c->err;
+            return rc_c;
+        }
+    }
     return BPB_OK;
 }
 
 int bpb_set_ms_scaling_factor(bpb_decoder *h, double v) {
     if (!h) return BPB_ERR_ARG;
     h->ms_scaling = v;
+    for (bpb_decoder *c: h->children) {
+        const int rc_c = bpb_set_ms_scaling_factor(c, v);
+        if (rc_c) {
+            h->err = c->err;
+            return rc_c;
+        }
+    }
     return BPB_OK;
 }
 
@@ -574,6 +657,7 @@ int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len)
     if (!order) {
         h->serial_order.clear();
         h->graph_dirty = true;
+        for (bpb_decoder *c: h->children) bpb_set_serial_schedule_order(c, nullptr, 0);
         return BPB_OK;
     }
     if (len < 0) return BPB_ERR_ARG;
@@ -584,16 +668,30 @@ int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len)
         }
     h->serial_order.assign(order, order + len);
     h->graph_dirty = true;
+    for (bpb_decoder *c: h->children) {
+        const int rc_c = bpb_set_serial_schedule_order(c, order, len);
+        if (rc_c) {
+            h->err = c->err;
+            return rc_c;
+        }
+    }
     return BPB_OK;
 }
 
 int bpb_set_kernel(bpb_decoder *h, int v) {
     if (!h) return BPB_ERR_ARG;
-    if (v != BPB_KERNEL_AUTO && v != BPB_KERNEL_STREAM && v != BPB_KERNEL_SMEM) {
+    if (v != BPB_KERNEL_AUTO && v != BPB_KERNEL_STREAM && v != BPB_KERNEL_SMEM && v != BPB_KERNEL_EDGE) {
         h->err = "invalid kernel family";
         return BPB_ERR_ARG;
     }
     h->kernel_pref = v;
+    for (bpb_decoder *c: h->children) {
+        const int rc_c = bpb_set_kernel(c, v);
+        if (rc_c) {
+            h->err = c->err;
+            return rc_c;
+        }
+    }
     return BPB_OK;
 }
 
@@ -609,26 +707,47 @@ int bpb_decode_batch_device(bpb_decoder *h, int input_type, const uint8_t *d_inp
         h->err = "invalid input type";
         return BPB_ERR_ARG;
     }
+    return decode_device_core(h, input_type, d_input, batch, d_decoding, d_converged, d_iterations, d_llr,
+                              (cudaStream_t) cuda_stream);
+}
+
+}  // extern "C"
+
+namespace {
+
+// input_type kInputPacked: d_input is already the bit-packed syndrome array [batch][mwp] (on-device producers)
+int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, int64_t batch, uint8_t *d_decoding,
+                       uint8_t *d_converged, int32_t *d_iterations, double *d_llr, cudaStream_t cuda_stream) {
+    int rc = BPB_OK;
     if (batch == 0) return BPB_OK;
     BPB_CUDA(h, cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t) cuda_stream;
+    cudaStream_t st = cuda_stream;
     if (h->graph_dirty) {
-        // the blob upload runs on the handle's own stream and is synchronised inside
+        // drains the device, uploads on the handle's own stream and synchronises inside
         if ((rc = upload_graph(h))) return rc;
     }
+    // The handle's workspaces (packed syndromes, counters, message tiles) are shared by consecutive calls: a call on
+    // another stream waits for the previous call's work.
+    if (h->have_last && h->last_stream != st) BPB_CUDA(h, cudaStreamWaitEvent(st, h->ev_last, 0));
     const bpb::HostGraph &g = h->g;
     const int mwp = round_up((g.m + 31) / 32, 4);
-    if ((rc = ensure(h, h->packed, (size_t) batch * mwp * 4))) return rc;
-    uint32_t *d_packed = (uint32_t *) h->packed.ptr;
+    const uint32_t *d_packed = reinterpret_cast<const uint32_t *>(d_input);
+    if (input_type != kInputPacked) {
+        if ((rc = ensure(h, h->packed, (size_t) batch * mwp * 4))) return rc;
+        d_packed = (const uint32_t *) h->packed.ptr;
+    }
+    h->last_packed = d_packed;
+    uint32_t *d_pack_out = (uint32_t *) h->packed.ptr;
     const int pgrid = (int) std::min<int64_t>((batch + 7) / 8, (int64_t) h->sm_count * 16);
-    if (input_type == BPB_INPUT_SYNDROME) {
-        pack_syndromes_kernel<<<pgrid, 256, 0, st>>>(d_input, batch, g.m, mwp, d_packed);
+    if (input_type == kInputPacked) {
+    } else if (input_type == BPB_INPUT_SYNDROME) {
+        pack_syndromes_kernel<<<pgrid, 256, 0, st>>>(d_input, batch, g.m, mwp, d_pack_out);
     } else {
         const uint32_t *blob = (const uint32_t *) h->blob.ptr;
-        pack_received_kernel<<<pgrid, 256, 0, st>>>(d_input, batch, g.m, g.n, mwp, blob, blob + (g.m + 1), d_packed);
+        pack_received_kernel<<<pgrid, 256, 0, st>>>(d_input, batch, g.m, g.n, mwp, blob, blob + (g.m + 1), d_pack_out);
     }
     BPB_CUDA(h, cudaGetLastError());
-    h->launches += 1;
+    if (input_type != kInputPacked) h->launches += 1;
     // family: the on-chip kernels serve the parallel schedule of codes whose messages fit in shared memory;
     // everything else (serial schedule, large codes) streams its messages through HBM.
     const bool smem_able = h->smem_plan.ok;
@@ -654,8 +773,202 @@ int bpb_decode_batch_device(bpb_decoder *h, int input_type, const uint8_t *d_inp
         BPB_CUDA(h, cudaGetLastError());
         h->launches += 1;
     }
+    BPB_CUDA(h, cudaEventRecord(h->ev_last, st));
+    h->last_stream = st;
+    h->have_last = true;
     return BPB_OK;
 }
+
+bool osd_on_device(const bpb_decoder *h) {
+    return h->osd_location != BPB_OSD_HOST && h->osd_plan.warps_per_cta > 0;
+}
+
+// BP + OSD-0 for one chunk that is already in device memory; everything is enqueued on `st`.
+// osd_count words: [0] failures of this chunk, [1] OSD work queue, [2] running total of the host call.
+int enqueue_bposd_device(bpb_decoder *h, const uint8_t *d_syn, int64_t nb, uint8_t *d_dec, uint8_t *d_conv,
+                         int32_t *d_its, uint8_t *d_bp_dec, cudaStream_t st, int input_type = BPB_INPUT_SYNDROME) {
+    const bpb::HostGraph &g = h->g;
+    int rc;
+    if ((rc = ensure(h, h->osd_llr, (size_t) nb * g.n * 8))) return rc;
+    if ((rc = ensure(h, h->osd_fail_idx, (size_t) nb * 4))) return rc;
+    if ((rc = ensure(h, h->osd_count, 64, true, st))) return rc;
+    if (!d_conv) {
+        if ((rc = ensure(h, h->osd_conv, (size_t) nb))) return rc;
+        d_conv = (uint8_t *) h->osd_conv.ptr;
+    }
+    h->llr_last_only = true;  // only syndromes that ran all maximum_iterations need their posterior LLRs
+    rc = decode_device_core(h, input_type, d_syn, nb, d_dec, d_conv, d_its, (double *) h->osd_llr.ptr, st);
+    h->llr_last_only = false;
+    if (rc) return rc;
+    if (d_bp_dec) BPB_CUDA(h, cudaMemcpyAsync(d_bp_dec, d_dec, (size_t) nb * g.n, cudaMemcpyDeviceToDevice, st));
+    unsigned long long *cnt = (unsigned long long *) h->osd_count.ptr;
+    BPB_CUDA(h, cudaMemsetAsync(cnt, 0, 16, st));
+    const int lgrid = (int) std::min<int64_t>((nb + 255) / 256, (int64_t) h->sm_count * 8);
+    list_failures_kernel<<<lgrid, 256, 0, st>>>(d_conv, nb, cnt, cnt + 2, (uint32_t *) h->osd_fail_idx.ptr);
+    BPB_CUDA(h, cudaGetLastError());
+    const uint32_t *blob = (const uint32_t *) h->blob.ptr;
+    const int mwp = round_up((g.m + 31) / 32, 4);
+    const int e = bpb::launch_osd0_kernel(h->osd_plan, g, h->sm_count, blob, blob + (g.m + 1),
+                                          h->last_packed, mwp, (const double *) h->osd_llr.ptr,
+                                          (const uint32_t *) h->osd_fail_idx.ptr, cnt, cnt + 1, d_dec, nb, st);
+    if (e) {
+        h->err = std::string("osd0_kernel launch: ") + cudaGetErrorString((cudaError_t) e);
+        return BPB_ERR_CUDA;
+    }
+    h->launches += 2;
+    BPB_CUDA(h, cudaEventRecord(h->ev_last, st));
+    return BPB_OK;
+}
+
+// memcpy on a few threads (one thread moves ~10 GB/s, the H2D link takes 25+)
+void parallel_copy(uint8_t *dst, const uint8_t *src, size_t bytes) {
+    const size_t min_part = (size_t) 4 << 20;
+    int parts = (int) std::min<size_t>(4, std::max<size_t>(1, bytes / min_part));
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw && (unsigned) parts > hw) parts = (int) hw;
+    if (parts <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < parts; t++) {
+        const size_t a = bytes * t / parts, b = bytes * (t + 1) / parts;
+        pool.emplace_back([=] { std::memcpy(dst + a, src + a, b - a); });
+    }
+    std::memcpy(dst, src, bytes / parts);
+    for (auto &th: pool) th.join();
+}
+
+// Rows per chunk of the host pipelines from a byte budget per staging slot (the fixed row counts of round 1 asked
+// for tens of GB at n = 10^4 with LLRs).
+int64_t chunk_rows(int64_t want, size_t row_bytes, int64_t batch) {
+    const size_t budget = (size_t) 2 << 30;
+    int64_t rows = (int64_t) (budget / std::max<size_t>(row_bytes, 1));
+    rows = std::max<int64_t>(rows, 1024);
+    rows = std::min<int64_t>(rows, want);
+    return std::max<int64_t>(1, std::min<int64_t>(rows, batch));
+}
+
+// Chunked three-stage pipeline (H2D | kernels | D2H) over two staging slots.  The on-chip family keeps no per-lane
+// state in HBM, so small chunks cost nothing; the streaming family amortises its persistent-lane ramp-down over large
+// chunks.  with_osd: BP + OSD-0 with the elimination on the device.
+int host_pipeline(bpb_decoder *h, int input_type, const uint8_t *input, int64_t batch, uint8_t *decoding,
+                  uint8_t *converged, int32_t *iterations, double *llr, uint8_t *bp_decoding, bool with_osd) {
+    const bpb::HostGraph &g = h->g;
+    int rc = BPB_OK;
+    const int in_w = (input_type == BPB_INPUT_RECEIVED_VECTOR) ? g.n : g.m;
+    const bool smem_able = h->smem_plan.ok && (h->kernel_pref == BPB_KERNEL_SMEM || h->kernel_pref == BPB_KERNEL_EDGE ||
+                                               (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
+    const size_t row_bytes = (size_t) in_w + (size_t) g.n * (bp_decoding ? 2 : 1) + 5 +
+                             ((llr || with_osd) ? (size_t) g.n * 8 : 0);
+    const int64_t chunk_max = chunk_rows(smem_able ? ((int64_t) 1 << 17) : ((int64_t) 1 << 20), row_bytes, batch);
+    const size_t cap = (size_t) chunk_max;
+    // Pageable input (e.g. a plain numpy array): cudaMemcpyAsync would go through the driver's single staging buffer
+    // at a few GB/s and block.  Stage it ourselves: a few host threads copy the chunk into a pinned slot buffer while
+    // the GPU works on the previous chunk, then a true asynchronous H2D follows.
+    bool stage_input = false;
+    {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, input) != cudaSuccess) cudaGetLastError();
+        else stage_input = (attr.type == cudaMemoryTypeUnregistered);
+    }
+    if (stage_input) {
+        for (int s = 0; s < 2; s++) {
+            if (h->pin_in_bytes[s] >= cap * (size_t) in_w) continue;
+            if (h->pin_in[s]) cudaFreeHost(h->pin_in[s]);
+            h->pin_in[s] = nullptr;
+            h->pin_in_bytes[s] = 0;
+            if (cudaHostAlloc(&h->pin_in[s], cap * (size_t) in_w, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                stage_input = false;  // cannot pin that much: let the driver stage
+                break;
+            }
+            h->pin_in_bytes[s] = cap * (size_t) in_w;
+        }
+    }
+    cudaError_t ce = cudaSuccess;
+    auto fail_cuda = [&](const char *what) {
+        h->err = std::string(what) + ": " + cudaGetErrorString(ce);
+        rc = BPB_ERR_CUDA;
+    };
+#define PIPE_CUDA(call)                 \
+    if (rc == BPB_OK) {                 \
+        ce = (call);                    \
+        if (ce != cudaSuccess) fail_cuda(#call); \
+    }
+    if (with_osd) {
+        if ((rc = ensure(h, h->osd_count, 64, true, h->stream))) return rc;
+        PIPE_CUDA(cudaMemsetAsync((unsigned long long *) h->osd_count.ptr + 2, 0, 8, h->stream));
+    }
+    int64_t c = 0;
+    for (int64_t lo = 0; lo < batch && rc == BPB_OK; lo += chunk_max, ++c) {
+        const int s = (int) (c & 1);
+        const int64_t nb = std::min(chunk_max, batch - lo);
+        if ((rc = ensure(h, h->st_in[s], cap * in_w))) break;
+        if ((rc = ensure(h, h->st_dec[s], cap * g.n))) break;
+        if ((rc = ensure(h, h->st_conv[s], cap))) break;
+        if ((rc = ensure(h, h->st_iters[s], cap * 4))) break;
+        if (llr && (rc = ensure(h, h->st_llr[s], cap * g.n * 8))) break;
+        if (bp_decoding && (rc = ensure(h, h->st_bp[s], cap * g.n))) break;
+        if (c >= 2) PIPE_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_k[s], 0));  // slot's input consumed
+        const uint8_t *src = input + lo * in_w;
+        if (stage_input) {
+            if (c >= 2) PIPE_CUDA(cudaEventSynchronize(h->ev_in[s]));  // the slot's previous H2D has left the buffer
+            parallel_copy((uint8_t *) h->pin_in[s], src, (size_t) nb * in_w);
+            src = (const uint8_t *) h->pin_in[s];
+        }
+        PIPE_CUDA(cudaMemcpyAsync(h->st_in[s].ptr, src, (size_t) nb * in_w, cudaMemcpyHostToDevice, h->s_in));
+        PIPE_CUDA(cudaEventRecord(h->ev_in[s], h->s_in));
+        PIPE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
+        if (c >= 2) PIPE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_out[s], 0));  // slot's outputs drained
+        if (rc) break;
+        if (with_osd)
+            rc = enqueue_bposd_device(h, (const uint8_t *) h->st_in[s].ptr, nb, (uint8_t *) h->st_dec[s].ptr,
+                                      (uint8_t *) h->st_conv[s].ptr, (int32_t *) h->st_iters[s].ptr,
+                                      bp_decoding ? (uint8_t *) h->st_bp[s].ptr : nullptr, h->stream);
+        else
+            rc = bpb_decode_batch_device(h, input_type, (const uint8_t *) h->st_in[s].ptr, nb,
+                                         (uint8_t *) h->st_dec[s].ptr, (uint8_t *) h->st_conv[s].ptr,
+                                         (int32_t *) h->st_iters[s].ptr, llr ? (double *) h->st_llr[s].ptr : nullptr,
+                                         h->stream);
+        if (rc) break;
+        PIPE_CUDA(cudaEventRecord(h->ev_k[s], h->stream));
+        PIPE_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_k[s], 0));
+        PIPE_CUDA(cudaMemcpyAsync(decoding + lo * g.n, h->st_dec[s].ptr, (size_t) nb * g.n, cudaMemcpyDeviceToHost,
+                                  h->s_out));
+        if (converged)
+            PIPE_CUDA(cudaMemcpyAsync(converged + lo, h->st_conv[s].ptr, (size_t) nb, cudaMemcpyDeviceToHost, h->s_out));
+        if (iterations)
+            PIPE_CUDA(cudaMemcpyAsync(iterations + lo, h->st_iters[s].ptr, (size_t) nb * 4, cudaMemcpyDeviceToHost,
+                                      h->s_out));
+        if (llr)
+            PIPE_CUDA(cudaMemcpyAsync(llr + lo * g.n, h->st_llr[s].ptr, (size_t) nb * g.n * 8, cudaMemcpyDeviceToHost,
+                                      h->s_out));
+        if (bp_decoding)
+            PIPE_CUDA(cudaMemcpyAsync(bp_decoding + lo * g.n, h->st_bp[s].ptr, (size_t) nb * g.n,
+                                      cudaMemcpyDeviceToHost, h->s_out));
+        PIPE_CUDA(cudaEventRecord(h->ev_out[s], h->s_out));
+    }
+#undef PIPE_CUDA
+    // also on the error path: no copy into the caller's memory may be in flight when this returns
+    cudaStreamSynchronize(h->s_in);
+    cudaError_t e1 = cudaStreamSynchronize(h->stream);
+    cudaError_t e2 = cudaStreamSynchronize(h->s_out);
+    if (rc == BPB_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        h->err = std::string("pipeline synchronise: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+        rc = BPB_ERR_CUDA;
+    }
+    if (rc == BPB_OK && with_osd) {
+        if (cudaMemcpy(h->host_counts, (unsigned long long *) h->osd_count.ptr + 2, 8, cudaMemcpyDeviceToHost) ==
+            cudaSuccess)
+            h->osd_device_solved += (int64_t) h->host_counts[0];
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
 
 int bpb_decode_batch(bpb_decoder *h, int input_type, const uint8_t *input, int64_t batch, uint8_t *decoding,
                      uint8_t *converged, int32_t *iterations, double *llr) {
@@ -666,55 +979,11 @@ int bpb_decode_batch(bpb_decoder *h, int input_type, const uint8_t *input, int64
         return BPB_ERR_ARG;
     }
     if (batch == 0) return BPB_OK;
+    if (!h->children.empty())
+        return multi_device_decode(h, input_type, input, batch, decoding, converged, iterations, llr, nullptr, false, 0);
     BPB_CUDA(h, cudaSetDevice(h->device));
     if (h->graph_dirty && (rc = upload_graph(h))) return rc;
-    const bpb::HostGraph &g = h->g;
-    const int in_w = (input_type == BPB_INPUT_RECEIVED_VECTOR) ? g.n : g.m;
-    // Chunked three-stage pipeline (H2D | kernels | D2H) over two staging slots.  The on-chip family keeps no
-    // per-lane state in HBM, so small chunks cost nothing; the streaming family amortises its persistent-lane
-    // ramp-down over large chunks.
-    const bool smem_able = h->smem_plan.ok && (h->kernel_pref == BPB_KERNEL_SMEM ||
-                                               (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
-    const int64_t chunk_max = smem_able ? ((int64_t) 1 << 17) : ((int64_t) 1 << 20);
-    int64_t c = 0;
-    for (int64_t lo = 0; lo < batch; lo += chunk_max, ++c) {
-        const int s = (int) (c & 1);
-        const int64_t nb = std::min(chunk_max, batch - lo);
-        const size_t cap = (size_t) std::min(chunk_max, batch);
-        if ((rc = ensure(h, h->st_in[s], cap * in_w))) return rc;
-        if ((rc = ensure(h, h->st_dec[s], cap * g.n))) return rc;
-        if ((rc = ensure(h, h->st_conv[s], cap))) return rc;
-        if ((rc = ensure(h, h->st_iters[s], cap * 4))) return rc;
-        if (llr && (rc = ensure(h, h->st_llr[s], cap * g.n * 8))) return rc;
-        if (c >= 2) BPB_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_k[s], 0));  // slot's input consumed
-        BPB_CUDA(h, cudaMemcpyAsync(h->st_in[s].ptr, input + lo * in_w, (size_t) nb * in_w, cudaMemcpyHostToDevice,
-                                    h->s_in));
-        BPB_CUDA(h, cudaEventRecord(h->ev_in[s], h->s_in));
-        BPB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
-        if (c >= 2) BPB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_out[s], 0));  // slot's outputs drained
-        rc = bpb_decode_batch_device(h, input_type, (const uint8_t *) h->st_in[s].ptr, nb,
-                                     (uint8_t *) h->st_dec[s].ptr, (uint8_t *) h->st_conv[s].ptr,
-                                     (int32_t *) h->st_iters[s].ptr, llr ? (double *) h->st_llr[s].ptr : nullptr,
-                                     h->stream);
-        if (rc) return rc;
-        BPB_CUDA(h, cudaEventRecord(h->ev_k[s], h->stream));
-        BPB_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_k[s], 0));
-        BPB_CUDA(h, cudaMemcpyAsync(decoding + lo * g.n, h->st_dec[s].ptr, (size_t) nb * g.n, cudaMemcpyDeviceToHost,
-                                    h->s_out));
-        if (converged)
-            BPB_CUDA(h, cudaMemcpyAsync(converged + lo, h->st_conv[s].ptr, (size_t) nb, cudaMemcpyDeviceToHost,
-                                        h->s_out));
-        if (iterations)
-            BPB_CUDA(h, cudaMemcpyAsync(iterations + lo, h->st_iters[s].ptr, (size_t) nb * 4,
-                                        cudaMemcpyDeviceToHost, h->s_out));
-        if (llr)
-            BPB_CUDA(h, cudaMemcpyAsync(llr + lo * g.n, h->st_llr[s].ptr, (size_t) nb * g.n * 8,
-                                        cudaMemcpyDeviceToHost, h->s_out));
-        BPB_CUDA(h, cudaEventRecord(h->ev_out[s], h->s_out));
-    }
-    BPB_CUDA(h, cudaStreamSynchronize(h->s_out));
-    BPB_CUDA(h, cudaStreamSynchronize(h->stream));
-    return BPB_OK;
+    return host_pipeline(h, input_type, input, batch, decoding, converged, iterations, llr, nullptr, false);
 }
 
 int bpb_osd0_host(bpb_decoder *h, const uint8_t *syndromes, const double *llr, const uint8_t *converged,
@@ -724,8 +993,10 @@ int bpb_osd0_host(bpb_decoder *h, const uint8_t *syndromes, const double *llr, c
         h->err = "bad osd arguments";
         return BPB_ERR_ARG;
     }
-    int rc = bpb::osd0_host(h->g, syndromes, llr, converged, batch, decoding, threads);
+    int64_t outside = 0;
+    int rc = bpb::osd0_host(h->g, syndromes, llr, converged, batch, decoding, threads, &outside);
     if (rc) h->err = "osd0_host failed";
+    h->osd_host_inconsistent += outside;
     return rc;
 }
 
@@ -738,10 +1009,21 @@ int bpb_bposd_decode_batch(bpb_decoder *h, const uint8_t *syndromes, int64_t bat
         return BPB_ERR_ARG;
     }
     if (batch == 0) return BPB_OK;
+    if (!h->children.empty())
+        return multi_device_decode(h, BPB_INPUT_SYNDROME, syndromes, batch, decoding, converged, iterations, nullptr,
+                                   bp_decoding, true, threads);
     BPB_CUDA(h, cudaSetDevice(h->device));
     if (h->graph_dirty && (rc = upload_graph(h))) return rc;
     const bpb::HostGraph &g = h->g;
-    const int64_t chunk_max = (int64_t) 1 << 17;
+    if (h->osd_location == BPB_OSD_DEVICE && h->osd_plan.warps_per_cta == 0) {
+        h->err = "OSD-0 on the device requested but this code does not fit the kernel (m > 1024 or matrix beyond shared memory)";
+        return BPB_ERR_UNSUPPORTED;
+    }
+    if (osd_on_device(h))
+        return host_pipeline(h, BPB_INPUT_SYNDROME, syndromes, batch, decoding, converged, iterations, nullptr,
+                             bp_decoding, true);
+    // host elimination: only the LLR rows of the non-converged syndromes cross PCIe
+    const int64_t chunk_max = chunk_rows((int64_t) 1 << 17, (size_t) g.n * 16 + g.m + g.n + 5, batch);
     const size_t cap = (size_t) std::min(chunk_max, batch);
     if ((rc = ensure(h, h->osd_llr, cap * g.n * 8))) return rc;
     if ((rc = ensure(h, h->osd_fail_llr, cap * g.n * 8))) return rc;
@@ -788,15 +1070,193 @@ int bpb_bposd_decode_batch(bpb_decoder *h, const uint8_t *syndromes, int64_t bat
             BPB_CUDA(h, cudaMemcpy(fllr.data(), h->osd_fail_llr.ptr, nfail * (size_t) g.n * 8, cudaMemcpyDeviceToHost));
             for (size_t q = 0; q < nfail; q++)
                 std::memcpy(&fsyn[q * g.m], syndromes + (lo + fidx[q]) * g.m, (size_t) g.m);
-            rc = bpb::osd0_host(g, fsyn.data(), fllr.data(), nullptr, (int64_t) nfail, fdec.data(), threads);
+            int64_t outside = 0;
+            rc = bpb::osd0_host(g, fsyn.data(), fllr.data(), nullptr, (int64_t) nfail, fdec.data(), threads, &outside);
+            h->osd_host_inconsistent += outside;
             if (rc) {
                 h->err = "osd0_host failed";
                 return rc;
             }
+            h->osd_host_solved += (int64_t) nfail;
             for (size_t q = 0; q < nfail; q++)
                 std::memcpy(decoding + (lo + fidx[q]) * g.n, &fdec[q * g.n], (size_t) g.n);
         }
     }
+    return BPB_OK;
+}
+
+int bpb_bposd_decode_batch_device(bpb_decoder *h, const uint8_t *d_syndromes, int64_t batch, uint8_t *d_decoding,
+                                  uint8_t *d_converged, int32_t *d_iterations, uint8_t *d_bp_decoding,
+                                  void *cuda_stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (batch < 0 || (batch > 0 && (!d_syndromes || !d_decoding))) {
+        h->err = "bad decode arguments";
+        return BPB_ERR_ARG;
+    }
+    if (batch == 0) return BPB_OK;
+    BPB_CUDA(h, cudaSetDevice(h->device));
+    if (h->graph_dirty && (rc = upload_graph(h))) return rc;
+    if (h->osd_plan.warps_per_cta == 0 || h->osd_location == BPB_OSD_HOST) {
+        h->err = "OSD-0 on the device is not available for this code / configuration";
+        return BPB_ERR_UNSUPPORTED;
+    }
+    return enqueue_bposd_device(h, d_syndromes, batch, d_decoding, d_converged, d_iterations, d_bp_decoding,
+                                (cudaStream_t) cuda_stream);
+}
+
+int bpb_mc_bsc(bpb_decoder *h, uint64_t seed, int64_t first_run, int64_t runs, const double *flip_prob, int with_osd,
+               int64_t counts[5]) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (runs < 0 || first_run < 0 || !counts) {
+        h->err = "bad Monte-Carlo arguments";
+        return BPB_ERR_ARG;
+    }
+    for (int i = 0; i < 5; i++) counts[i] = 0;
+    if (runs == 0) return BPB_OK;
+    const bpb::HostGraph &g = h->g;
+    if (!h->children.empty()) {
+        // runs split contiguously over the devices; run numbers (hence the drawn errors) do not depend on the split
+        const int k = (int) h->children.size();
+        std::vector<int> rcs((size_t) k, BPB_OK);
+        std::vector<std::vector<int64_t>> part((size_t) k, std::vector<int64_t>(5, 0));
+        auto work = [&](int r) {
+            const int64_t lo = runs * r / k, hi = runs * (r + 1) / k;
+            if (hi > lo)
+                rcs[(size_t) r] = bpb_mc_bsc(h->children[(size_t) r], seed, first_run + lo, hi - lo, flip_prob, with_osd,
+                                             part[(size_t) r].data());
+        };
+        std::vector<std::thread> pool;
+        for (int r = 1; r < k; r++) pool.emplace_back(work, r);
+        work(0);
+        for (auto &t: pool) t.join();
+        for (int r = 0; r < k; r++) {
+            if (rcs[(size_t) r]) {
+                h->err = "device slice " + std::to_string(r) + ": " + h->children[(size_t) r]->err;
+                return rcs[(size_t) r];
+            }
+            for (int i = 0; i < 5; i++) counts[i] += part[(size_t) r][(size_t) i];
+        }
+        return BPB_OK;
+    }
+    BPB_CUDA(h, cudaSetDevice(h->device));
+    if (h->graph_dirty && (rc = upload_graph(h))) return rc;
+    if (with_osd && !osd_on_device(h)) {
+        h->err = "bpb_mc_bsc with OSD-0 needs the device OSD-0 kernel, which is not available for this code";
+        return BPB_ERR_UNSUPPORTED;
+    }
+    std::vector<unsigned long long> thresh((size_t) g.n);
+    for (int j = 0; j < g.n; j++) {
+        double p = flip_prob ? flip_prob[j] : h->channel[(size_t) j];
+        if (!(p >= 0.0)) p = 0.0;
+        if (p > 1.0) p = 1.0;
+        thresh[(size_t) j] = (unsigned long long) (p * 4294967296.0);
+    }
+    cudaStream_t st = h->stream;
+    if ((rc = ensure(h, h->mc_thresh, (size_t) g.n * 8))) return rc;
+    BPB_CUDA(h, cudaMemcpyAsync(h->mc_thresh.ptr, thresh.data(), (size_t) g.n * 8, cudaMemcpyHostToDevice, st));
+    const int nw = (g.n + 31) / 32, mwp = round_up((g.m + 31) / 32, 4);
+    const size_t row_bytes = (size_t) g.n + (size_t) nw * 4 + (size_t) mwp * 4 + 5 + (with_osd ? (size_t) g.n * 8 : 0);
+    const int64_t chunk = chunk_rows((int64_t) 1 << 20, row_bytes, runs);
+    if ((rc = ensure(h, h->mc_err, (size_t) chunk * nw * 4))) return rc;
+    if ((rc = ensure(h, h->mc_syn, (size_t) chunk * mwp * 4))) return rc;
+    if ((rc = ensure(h, h->mc_dec, (size_t) chunk * g.n))) return rc;
+    if ((rc = ensure(h, h->mc_conv, (size_t) chunk))) return rc;
+    if ((rc = ensure(h, h->mc_its, (size_t) chunk * 4))) return rc;
+    if ((rc = ensure(h, h->mc_counts, 64))) return rc;
+    BPB_CUDA(h, cudaMemsetAsync(h->mc_counts.ptr, 0, 64, st));
+    const uint32_t *blob = (const uint32_t *) h->blob.ptr;
+    for (int64_t lo = 0; lo < runs; lo += chunk) {
+        const int64_t nb = std::min(chunk, runs - lo);
+        int e = bpb::launch_mc_generate(blob, blob + (g.m + 1), (const unsigned long long *) h->mc_thresh.ptr, g.m, g.n,
+                                        nw, mwp, seed, (unsigned long long) (first_run + lo), nb,
+                                        (uint32_t *) h->mc_err.ptr, (uint32_t *) h->mc_syn.ptr, h->sm_count, st);
+        if (e) {
+            h->err = std::string("mc_generate_kernel: ") + cudaGetErrorString((cudaError_t) e);
+            return BPB_ERR_CUDA;
+        }
+        if (with_osd)
+            rc = enqueue_bposd_device(h, (const uint8_t *) h->mc_syn.ptr, nb, (uint8_t *) h->mc_dec.ptr,
+                                      (uint8_t *) h->mc_conv.ptr, (int32_t *) h->mc_its.ptr, nullptr, st, kInputPacked);
+        else
+            rc = decode_device_core(h, kInputPacked, (const uint8_t *) h->mc_syn.ptr, nb, (uint8_t *) h->mc_dec.ptr,
+                                    (uint8_t *) h->mc_conv.ptr, (int32_t *) h->mc_its.ptr, nullptr, st);
+        if (rc) return rc;
+        e = bpb::launch_mc_score((const uint8_t *) h->mc_dec.ptr, (const uint32_t *) h->mc_err.ptr,
+                                 (const uint8_t *) h->mc_conv.ptr, (const int32_t *) h->mc_its.ptr, g.n, nw, nb,
+                                 (unsigned long long *) h->mc_counts.ptr, h->sm_count, st);
+        if (e) {
+            h->err = std::string("mc_score_kernel: ") + cudaGetErrorString((cudaError_t) e);
+            return BPB_ERR_CUDA;
+        }
+        h->launches += 2;
+    }
+    unsigned long long host[5] = {0, 0, 0, 0, 0};
+    BPB_CUDA(h, cudaMemcpyAsync(host, h->mc_counts.ptr, sizeof(host), cudaMemcpyDeviceToHost, st));
+    BPB_CUDA(h, cudaStreamSynchronize(st));
+    counts[0] = (int64_t) host[4];
+    counts[1] = (int64_t) host[0];
+    counts[2] = (int64_t) host[1];
+    counts[3] = (int64_t) host[2];
+    counts[4] = (int64_t) host[3];
+    return BPB_OK;
+}
+
+int bpb_set_devices(bpb_decoder *h, const int *ids, int count) {
+    if (!h) return BPB_ERR_ARG;
+    if (h->device < 0) {
+        h->err = "host-only handle";
+        return BPB_ERR_CUDA;
+    }
+    if (count < 0 || (count > 0 && !ids)) {
+        h->err = "bad device list";
+        return BPB_ERR_ARG;
+    }
+    for (bpb_decoder *c: h->children) bpb_destroy(c);
+    h->children.clear();
+    if (count == 0) return BPB_OK;
+    const bpb::HostGraph &g = h->g;
+    std::vector<int32_t> rows((size_t) g.nnz), cols((size_t) g.nnz);
+    for (int i = 0; i < g.m; i++)
+        for (uint32_t e = g.row_ptr[(size_t) i]; e < g.row_ptr[(size_t) i + 1]; e++) {
+            rows[e] = i;
+            cols[e] = (int32_t) g.col_idx[e];
+        }
+    for (int k = 0; k < count; k++) {
+        bpb_decoder *c = nullptr;
+        int rc = bpb_create(g.m, g.n, g.nnz, rows.data(), cols.data(), ids[k], &c);
+        if (rc == BPB_OK && !h->channel.empty()) rc = bpb_set_channel(c, h->channel.data(), g.n);
+        if (rc == BPB_OK) {
+            c->max_iter = h->max_iter;
+            c->method = h->method;
+            c->schedule = h->schedule;
+            c->ms_scaling = h->ms_scaling;
+            c->serial_order = h->serial_order;
+            c->kernel_pref = h->kernel_pref;
+            c->osd_location = h->osd_location;
+            c->graph_dirty = true;
+            h->children.push_back(c);
+        } else {
+            h->err = std::string("bpb_set_devices: device ") + std::to_string(ids[k]) + ": " +
+                     (c ? c->err : std::string(bpb_last_error(nullptr)));
+            if (c) bpb_destroy(c);
+            for (bpb_decoder *d: h->children) bpb_destroy(d);
+            h->children.clear();
+            return rc;
+        }
+    }
+    return BPB_OK;
+}
+
+int bpb_set_osd_location(bpb_decoder *h, int v) {
+    if (!h) return BPB_ERR_ARG;
+    if (v != BPB_OSD_AUTO && v != BPB_OSD_HOST && v != BPB_OSD_DEVICE) {
+        h->err = "invalid OSD location";
+        return BPB_ERR_ARG;
+    }
+    h->osd_location = v;
+    for (bpb_decoder *c: h->children) c->osd_location = v;
     return BPB_OK;
 }
 
@@ -832,6 +1292,16 @@ int bpb_get_info(const bpb_decoder *h_, bpb_info *out) {
             out->stream_iterations = (int64_t) words[3];
         }
     }
+    out->osd_device_available = (h->device >= 0 && !h->graph_dirty) ? (h->osd_plan.warps_per_cta > 0)
+                                                                    : (bpb::plan_osd_device(h->g, h->max_smem_optin > 0 ? h->max_smem_optin : 232448).warps_per_cta > 0);
+    out->osd_device_solved = h->osd_device_solved;
+    out->osd_host_solved = h->osd_host_solved;
+    out->osd_host_inconsistent = h->osd_host_inconsistent;
+    for (const bpb_decoder *c: h->children) {
+        out->osd_device_solved += c->osd_device_solved;
+        out->osd_host_solved += c->osd_host_solved;
+        out->launches += c->launches;
+    }
     out->smem_family_available = h->smem_plan.ok ? 1 : 0;
     out->smem_bank_multiplicity = h->smem_plan.max_bank_multiplicity;
     out->smem_bytes_per_syndrome = (int) h->smem_plan.group_bytes;
@@ -854,3 +1324,47 @@ void bpb_host_free(void *p) {
 }
 
 }  // extern "C"
+
+namespace {
+
+// bpb_set_devices: contiguous slices of one host batch, one host thread per device, each through that device's own
+// pipeline; outputs land in disjoint ranges of the caller's arrays.
+int multi_device_decode(bpb_decoder *h, int input_type, const uint8_t *input, int64_t batch, uint8_t *decoding,
+                        uint8_t *converged, int32_t *iterations, double *llr, uint8_t *bp_decoding, bool osd,
+                        int threads) {
+    const int k = (int) h->children.size();
+    const bpb::HostGraph &g = h->g;
+    const int in_w = (input_type == BPB_INPUT_RECEIVED_VECTOR) ? g.n : g.m;
+    std::vector<int> rcs((size_t) k, BPB_OK);
+    auto work = [&](int r) {
+        const int64_t lo = batch * r / k, hi = batch * (r + 1) / k;
+        if (hi <= lo) return;
+        bpb_decoder *c = h->children[(size_t) r];
+        const int64_t nb = hi - lo;
+        if (osd)
+            rcs[(size_t) r] = bpb_bposd_decode_batch(c, input + lo * in_w, nb, decoding + lo * g.n,
+                                                     converged ? converged + lo : nullptr,
+                                                     iterations ? iterations + lo : nullptr,
+                                                     bp_decoding ? bp_decoding + lo * g.n : nullptr,
+                                                     threads > 0 ? std::max(1, threads / k) : 0);
+        else
+            rcs[(size_t) r] = bpb_decode_batch(c, input_type, input + lo * in_w, nb, decoding + lo * g.n,
+                                               converged ? converged + lo : nullptr,
+                                               iterations ? iterations + lo : nullptr, llr ? llr + lo * g.n : nullptr);
+    };
+    std::vector<std::thread> pool;
+    for (int r = 1; r < k; r++) pool.emplace_back(work, r);
+    work(0);
+    for (auto &t: pool) t.join();
+    for (int r = 0; r < k; r++)
+        if (rcs[(size_t) r]) {
+            h->err = "device slice " + std::to_string(r) + ": " + h->children[(size_t) r]->err;
+            return rcs[(size_t) r];
+        }
+    h->last_family = h->children[0]->last_family;
+    h->last_grid = h->children[0]->last_grid;
+    h->last_block = h->children[0]->last_block;
+    return BPB_OK;
+}
+
+}  // namespace

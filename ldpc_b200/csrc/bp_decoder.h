@@ -25,7 +25,7 @@ int build_host_graph(int m, int n, int64_t nnz, const int32_t *rows, const int32
 
 // Bit-packed OSD-0 on the host (osd_host.cpp).
 int osd0_host(const HostGraph &g, const uint8_t *syndromes, const double *llr, const uint8_t *converged,
-              int64_t batch, uint8_t *decoding, int threads);
+              int64_t batch, uint8_t *decoding, int threads, int64_t *inconsistent = nullptr);
 
 struct DeviceBuffer {
     void *ptr = nullptr;
@@ -46,6 +46,25 @@ struct SmemPlan {
     uint32_t group_bytes = 0, goff_msg = 0, goff_dec = 0, goff_syn = 0, goff_ctl = 0;
     int M = 0, N = 0;
 };
+
+// Device OSD-0 (osd_device.cu): per-warp shared-memory plan; warps_per_cta == 0 when the code does not fit.
+struct OsdDevicePlan {
+    int warps_per_cta = 0;
+    int depth = 0, ws = 0, rows_per_lane = 0;
+    uint32_t warp_bytes = 0, off_a = 0, off_b = 0, off_inv = 0, off_piv = 0;
+};
+OsdDevicePlan plan_osd_device(const HostGraph &g, int max_smem_optin);
+int launch_osd0_kernel(const OsdDevicePlan &pl, const HostGraph &g, int sm_count, const uint32_t *d_row_ptr,
+                       const uint32_t *d_col_idx, const uint32_t *d_packed, int mwp, const double *d_llr,
+                       const uint32_t *d_fail_idx, const unsigned long long *d_count, unsigned long long *d_counter,
+                       uint8_t *d_dec, int64_t max_items, cudaStream_t st);
+
+// On-device BSC sampling and scoring (mc_device.cu)
+int launch_mc_generate(const uint32_t *d_row_ptr, const uint32_t *d_col_idx, const unsigned long long *d_thresh, int m,
+                       int n, int nw, int mwp, unsigned long long seed, unsigned long long first_run, int64_t batch,
+                       uint32_t *d_err, uint32_t *d_syn, int sm_count, cudaStream_t st);
+int launch_mc_score(const uint8_t *d_dec, const uint32_t *d_err, const uint8_t *d_conv, const int32_t *d_iters, int n,
+                    int nw, int64_t batch, unsigned long long *d_counts, int sm_count, cudaStream_t st);
 
 }  // namespace bpb
 
@@ -79,9 +98,22 @@ struct bpb_decoder {
     bool graph_dirty = true;  // blob must be (re)uploaded (prior or order changed)
     bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed, smem_tab, handoff;
     bpb::DeviceBuffer osd_llr, osd_fail_llr, osd_fail_idx, osd_count;  // BP+OSD batch path
+    bpb::OsdDevicePlan osd_plan;
+    bpb::DeviceBuffer mc_thresh, mc_err, mc_syn, mc_dec, mc_conv, mc_its, mc_counts;  // bpb_mc_bsc workspaces
+    int osd_location = BPB_OSD_AUTO;  // where OSD-0 runs in the BP+OSD entry points
+    bool llr_last_only = false;       // BP+OSD: posterior LLRs are only needed for syndromes that ran max_iter
+    int64_t osd_device_solved = 0, osd_host_solved = 0, osd_host_inconsistent = 0;
+    cudaEvent_t ev_last = nullptr;    // recorded after the last enqueue of bpb_decode_batch_device
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
+    const uint32_t *last_packed = nullptr;  // packed syndromes of the last decode (the OSD-0 kernel reads them)
+    void *pin_in[2] = {nullptr, nullptr};  // pinned staging for pageable host input (host_pipeline)
+    size_t pin_in_bytes[2] = {0, 0};
+    unsigned long long *host_counts = nullptr;  // pinned: failure counts of the two pipeline slots
     bpb::SmemPlan smem_plan;
     // staging for the host API
-    bpb::DeviceBuffer st_in[2], st_dec[2], st_conv[2], st_iters[2], st_llr[2];
+    bpb::DeviceBuffer st_in[2], st_dec[2], st_conv[2], st_iters[2], st_llr[2], st_bp[2], osd_conv;
+    std::vector<bpb_decoder *> children;  // bpb_set_devices: one full decoder per device, this handle only splits
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host API pipeline
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     uint32_t blob_words = 0, prior_off = 0;

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_kernel(const SmemParams p) {
                     for (int k = 0; k < DV; ++k)
                         if (k < deg) msg[pos[k]] = c[k];
                     x = (llr <= 0);
-                    if (LLR) p.out_llr[idx * n + j] = llr;
+                    if (LLR && (!p.llr_last_only || it == p.max_iter)) p.out_llr[idx * n + j] = llr;
                     if (x) {
                         // bp.hpp:290-294: a decided-1 bit flips the candidate syndrome of its checks
 #pragma unroll

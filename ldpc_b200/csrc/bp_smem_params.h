@@ -29,6 +29,7 @@ struct SmemParams {
     uint8_t *out_conv;    // [B] or null
     int32_t *out_iters;   // [B] or null
     double *out_llr;      // [B][n] or null
+    int llr_last_only;    // BP+OSD: write posterior LLRs only in iteration max_iter (only non-convergers need them)
 };
 
 using SmemKernel = void (*)(const SmemParams);

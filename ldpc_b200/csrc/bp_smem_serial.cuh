@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_smem_serial_kernel(const SmemParam
                     for (int k = 0; k < DV; ++k)
                         if (k < deg) msg[pe[k]] = c[k];
                     const bool x = (L <= 0);
-                    if (LLR) p.out_llr[idx * n + j] = L;
+                    if (LLR && (!p.llr_last_only || it == p.max_iter)) p.out_llr[idx * n + j] = L;
                     dec[j] = x ? 1 : 0;
                 }
                 group_sync(bar, T);

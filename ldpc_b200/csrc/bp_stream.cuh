@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParalle
                 if (p.out_iters) p.out_iters[oidx] = oit;
                 if (p.out_conv) p.out_conv[oidx] = (uint8_t) oconv;
             }
-            if (LLR) {
+            if (LLR && !(p.llr_last_only && oconv)) {
                 const double *src = p.llr_tile + (size_t) gw * (size_t) n * 32 + l;
                 double *dst = p.out_llr + oidx * n;
                 for (int j = lane; j < n; j += 32) dst[j] = __ldcg(src + (size_t) j * 32);

@@ -27,6 +27,7 @@ struct StreamParams {
     uint8_t *out_conv;    // [B] or null
     int32_t *out_iters;   // [B] or null
     double *out_llr;      // [B][n] or null
+    int llr_last_only;    // BP+OSD: copy posterior LLRs out only for syndromes that did not converge
     const uint32_t *order;  // serial schedule: levelised batches of SerialBatch bits, 0xffffffff = padding
     int order_len;
     int iter_cap;                       // hand-off threshold (>= max_iter disables the second stage)

@@ -13,7 +13,17 @@
 // solution supported on independent columns is unique.  So this is a from-scratch bit-packed column
 // elimination: each incoming column is reduced against the pivots found so far (64 rows per XOR), the
 // syndrome is reduced alongside, and the combination is unwound at the end.
+//
+// Syndromes OUTSIDE the image of H (possible only with redundant checks and measurement noise that H does not model;
+// s = H e is always inside): the sweep ends with a non-zero residual.  The reference then returns the solution of the
+// equations of ITS pivot rows, which it picks by smallest row weight with ties broken by the order of a linked list
+// that row swaps leave unsorted (gf2sparse_linalg.hpp:331-353, sparse_matrix_base.hpp:284-300) -- an artefact of its
+// data structure, not of OSD.  Here (and in the device kernel, osd_device.cu) the result for such a syndrome is the
+// unique solution on the same pivot COLUMNS of the equations of the lowest-index independent rows; it differs from
+// the reference's in general.  osd0_host counts these syndromes (returned through `inconsistent`), the Python layer
+// exposes the count, and tests/test_host_api.py::test_osd0_random_syndromes_bb144 pins both behaviours.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -61,7 +71,8 @@ inline bool any_set(const std::vector<uint64_t> &a) {
     return false;
 }
 
-void osd0_one(const HostGraph &g, Workspace &ws, const uint8_t *syn, const double *llr, uint8_t *out) {
+// returns true when the syndrome turned out to lie outside the image of H
+bool osd0_one(const HostGraph &g, Workspace &ws, const uint8_t *syn, const double *llr, uint8_t *out) {
     const int m = ws.m, n = ws.n, mw = ws.mw;
     for (int j = 0; j < n; j++) {
         ws.recs[(size_t) j].value = llr[j];
@@ -117,12 +128,14 @@ void osd0_one(const HostGraph &g, Workspace &ws, const uint8_t *syn, const doubl
             for (int w = 0; w <= (k >> 6); w++) ws.yu[(size_t) w] ^= uk[w];
         }
     }
+    return any_set(ws.y);
 }
 
 }  // namespace
 
 int osd0_host(const HostGraph &g, const uint8_t *syndromes, const double *llr, const uint8_t *converged,
-              int64_t batch, uint8_t *decoding, int threads) {
+              int64_t batch, uint8_t *decoding, int threads, int64_t *inconsistent) {
+    std::atomic<int64_t> outside{0};
     std::vector<int64_t> todo;
     for (int64_t b = 0; b < batch; b++)
         if (!converged || !converged[b]) todo.push_back(b);
@@ -134,7 +147,7 @@ int osd0_host(const HostGraph &g, const uint8_t *syndromes, const double *llr, c
         Workspace ws(g.m, g.n);
         for (size_t q = (size_t) t; q < todo.size(); q += (size_t) threads) {
             const int64_t b = todo[q];
-            osd0_one(g, ws, syndromes + b * g.m, llr + b * g.n, decoding + b * g.n);
+            if (osd0_one(g, ws, syndromes + b * g.m, llr + b * g.n, decoding + b * g.n)) outside++;
         }
     };
     if (threads == 1) {
@@ -144,6 +157,7 @@ int osd0_host(const HostGraph &g, const uint8_t *syndromes, const double *llr, c
         for (int t = 0; t < threads; t++) pool.emplace_back(run, t);
         for (auto &th: pool) th.join();
     }
+    if (inconsistent) *inconsistent = outside.load();
     return BPB_OK;
 }
 

@@ -21,7 +21,7 @@ import scipy.sparse as sp
 class MonteCarloBscSimulation:
     def __init__(self, parity_check_matrix: Union[np.ndarray, sp.csr_matrix] = None, error_rate: float = None,
                  Decoder=None, target_run_count=1000, tqdm_disable=False, save_interval=60, seed=None, run=False,
-                 batch_size: int = 1 << 16) -> None:
+                 batch_size: int = 1 << 16, device_side: bool = False) -> None:
         if parity_check_matrix is None or not isinstance(parity_check_matrix, (np.ndarray, sp.csr_matrix)):
             raise ValueError(
                 f"parity_check_matrix should be of type np.ndarray or scipy.sparse.csr_matrix. Not {type(parity_check_matrix)}")
@@ -44,6 +44,9 @@ class MonteCarloBscSimulation:
         if not isinstance(batch_size, int) or batch_size <= 0:
             raise ValueError("Invalid batch size provided.")
         self.batch_size = batch_size
+        # device_side: errors are drawn, turned into syndromes, decoded and scored on the GPU (Decoder.monte_carlo_bsc,
+        # Philox4x32-10 keyed by `seed`); only counters come back.  The drawn errors then differ from numpy's.
+        self.device_side = bool(device_side)
         if seed is None:
             self.seed = None
         else:
@@ -64,6 +67,16 @@ class MonteCarloBscSimulation:
         n = H.shape[1]
         self.fail_count = 0
         done = self.run_count
+        if self.device_side:
+            r = self.Decoder.monte_carlo_bsc(self.target_run_count - done, seed=0 if self.seed is None else self.seed,
+                                             error_rate=self.error_rate, first_run=done,
+                                             with_osd=hasattr(self.Decoder, "osd_method"))
+            self.fail_count = r["fail_count"]
+            self.run_count = done + r["run_count"]
+            self.logical_error_rate = self.fail_count / self.run_count
+            self.logical_error_rate_eb = np.sqrt(
+                self.logical_error_rate * (1 - self.logical_error_rate) / self.run_count)
+            return self.save()
         while done < self.target_run_count:
             nb = min(self.batch_size, self.target_run_count - done)
             # the reference's generate_bsc_error (noise_models/bsc.py:23), nb runs at once

@@ -4,15 +4,14 @@ The decode of one syndrome never touches another (reference src_cpp/bp.hpp:192-3
 per call), so the batch splits into contiguous shards with no collective on the data path (BASELINE.json
 north_star: "host-side split and final gather, NCCL not on the hot path").  Two ways to drive it:
 
-* ``MultiGpuBpDecoder``  -- one process, one ``BpDecoder`` (one C-ABI handle) per device, one host thread per
-  device; the ctypes call releases the GIL, so the shards decode concurrently and write into disjoint slices of
-  one host output array (that *is* the gather).
+* ``MultiGpuBpDecoder``  -- one process, ONE C-ABI handle split over the devices by ``bpb_set_devices``: a host
+  thread and a chunked H2D | kernels | D2H pipeline per device, results written into disjoint slices of one host
+  output array (that *is* the gather).
 * ``decode_sharded``     -- one process per GPU (torchrun): every rank decodes its own shard; rank 0 can collect
   the pieces with ``torch.distributed`` (gloo or nccl) after the timed region.
 """
 from __future__ import annotations
 
-import threading
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -28,47 +27,27 @@ def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 class MultiGpuBpDecoder:
-    """Host-side split of one batch over several devices of one box (single process, one thread per device)."""
+    """Host-side split of one batch over several devices of one box, done INSIDE the library: one C-ABI handle with
+    ``bpb_set_devices`` (one full decoder, pinned-speed staging and host thread per device; contiguous input slices,
+    outputs copied into disjoint ranges of one host array).  Equivalent to ``BpDecoder(pcm, devices=[...])``."""
 
     def __init__(self, pcm, devices: Sequence[int], **kwargs):
         from .bp_decoder import BpDecoder
         if len(devices) < 1:
             raise ValueError("need at least one device")
-        self.devices = list(devices)
-        self.decoders = [BpDecoder(pcm, device=int(d), **kwargs) for d in self.devices]
-        self.n = self.decoders[0].n
+        self.devices = [int(d) for d in devices]
+        self.decoder = BpDecoder(pcm, devices=self.devices, **kwargs)
+        self.n = self.decoder.n
         self.converge_batch = None
         self.iter_batch = None
 
     def decode_batch(self, syndromes: np.ndarray) -> np.ndarray:
-        syn = np.ascontiguousarray(np.asarray(syndromes).astype(np.uint8, copy=False))
-        B = syn.shape[0]
-        out = np.empty((B, self.n), dtype=np.uint8)
-        conv = np.empty(B, dtype=bool)
-        its = np.empty(B, dtype=np.int32)
-        errors: List[Optional[BaseException]] = [None] * len(self.decoders)
-
-        def work(r: int):
-            try:
-                lo, hi = shard_bounds(B, len(self.decoders), r)
-                if hi > lo:
-                    d = self.decoders[r]
-                    out[lo:hi] = d.decode_batch(syn[lo:hi])
-                    conv[lo:hi] = d.converge_batch
-                    its[lo:hi] = d.iter_batch
-            except BaseException as e:  # noqa: BLE001
-                errors[r] = e
-
-        threads = [threading.Thread(target=work, args=(r,)) for r in range(len(self.decoders))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        for e in errors:
-            if e is not None:
-                raise e
-        self.converge_batch, self.iter_batch = conv, its
+        out = self.decoder.decode_batch(syndromes)
+        self.converge_batch, self.iter_batch = self.decoder.converge_batch, self.decoder.iter_batch
         return out
+
+    def monte_carlo_bsc(self, runs: int, **kw) -> dict:
+        return self.decoder.monte_carlo_bsc(runs, **kw)
 
 
 def decode_sharded(decode_fn: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray, np.ndarray]],

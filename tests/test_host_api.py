@@ -247,6 +247,46 @@ def test_host_osd0_matches_oracle_and_reference(port_oracle, ref_oracle, threads
         assert np.array_equal(out[~conv], port_oracle.osd0_batch(H, syn[~conv], llr[~conv]))
 
 
+def test_osd0_random_syndromes_bb144(ref_oracle):
+    """Random syndromes on a rank-deficient H (bb144: rank 66 of 72 rows) with the reference's own LLRs.  Rows whose
+    syndrome lies in the image of H must equal the reference's OsdDecoder output; for the others the reference's
+    answer depends on its linked-list pivot-row order (documented divergence, osd_host.cpp header): here the result
+    solves the equations of the pivot rows it picked and the library counts them (`osd_host_inconsistent`)."""
+    H = codes.bivariate_bicycle_144()
+    m, n = H.shape
+    rng = np.random.default_rng(99)
+    B = 400
+    syn = rng.integers(0, 2, size=(B, m)).astype(np.uint8)
+    syn[: B // 2] = codes.bsc_syndromes(H, 0.05, B // 2, seed=3)  # half of them are genuine s = H e
+    kw = dict(max_iter=15, bp_method="ms", ms_scaling_factor=0.625)
+    dec, conv, its, llr, bpdec = ref_oracle.decode_batch(H, syn, 0.05, osd_method=1, osd_order=0, **kw)
+    lib, h = _host_only_handle(H)
+    out = bpdec.copy()
+    rc = lib.bpb_osd0_host(h, _capi.host_ptr(syn), _capi.host_ptr(llr), _capi.host_ptr(conv.astype(np.uint8)), B,
+                           _capi.host_ptr(out), 2)
+    assert rc == 0
+    inf = _capi.BpbInfo()
+    assert lib.bpb_get_info(h, C.byref(inf)) == 0
+    lib.bpb_destroy(h)
+    in_image = (codes.syndromes_of(H, dec) == syn).all(axis=1)  # the reference solved it <=> it is solvable
+    assert in_image[: B // 2].all() and 0 < (~in_image).sum()
+    assert np.array_equal(out[in_image], dec[in_image])
+    assert inf.osd_host_inconsistent == int((~in_image & ~conv).sum())
+    # outside the image: still a deterministic answer supported on at most rank(H) columns
+    assert out[~in_image].sum(axis=1).max() <= 66
+
+
+def test_osd_column_order_is_the_libc_qsort_merge_tree(tmp_path):
+    """ldpc_b200/csrc/osd_order.h (what the device OSD-0 kernel walks) against the live libc qsort with the reference's
+    record layout and comparator (sort.hpp:27-62): ties, +-0, +-inf and NaN keys."""
+    import subprocess
+    exe = str(tmp_path / "osd_order_check")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "osd_order_check.c")
+    subprocess.run(["gcc", "-O2", "-o", exe, src], check=True)
+    res = subprocess.run([exe, "3000"], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.startswith("0 orders differ"), res.stdout
+
+
 @pytest.mark.parametrize("mk", [lambda: codes.regular_ldpc(1000, 3, 6, seed=1), codes.bivariate_bicycle_144,
                                 lambda: codes.rotated_surface_code_x(13), lambda: codes.hamming_code(5),
                                 lambda: codes.rep_code(40)], ids=["ldpc1000", "bb144", "surface13", "hamming5", "rep40"])
