@@ -481,7 +481,8 @@ def run_ours(args, cfg, rank, local_rank, world):
         o_s = max_over_ranks(time.perf_counter() - t0)
         e2e_bposd = {"value": B * world / o_s, "unit": "decodes/s", "seconds": o_s,
                      "api": "bpb_bposd_decode_batch (BP + OSD-0 for the non-converged rows), pinned host buffers",
-                     "non_converged_fraction": 1.0 - conv_frac, "osd": od.info().get("osd_location", "host")}
+                     "non_converged_fraction": 1.0 - conv_frac,
+                     "osd": "device" if od.info().get("osd_device_solved", 0) > 0 else "host"}
         del od
 
     # ---- reference C++ on this box's host cores, bounded sample of the SAME batch (rank 0, N = 1 only) ------------

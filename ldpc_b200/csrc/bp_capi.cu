@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "bp_decoder.h"
+#include "bp_edge_params.h"
 #include "bp_smem_params.h"
 #include "bp_stream_params.h"
 
@@ -52,7 +53,7 @@ std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
             &h->packed,   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
             &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1],
             &h->st_bp[0],   &h->st_bp[1],   &h->osd_conv,  &h->mc_thresh, &h->mc_err, &h->mc_syn, &h->mc_dec,
-            &h->mc_conv,    &h->mc_its,     &h->mc_counts};
+            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg};
 }
 
 void release(bpb::DeviceBuffer &b) {
@@ -238,6 +239,11 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
                 int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
                 const unsigned long long *batch_dev);
 
+bool edge_able(const bpb_decoder *h);
+int launch_edge(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
+                int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
+                const unsigned long long *batch_dev);
+
 int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
                   int32_t *d_iters, double *d_llr, cudaStream_t st) {
     const bpb::HostGraph &g = h->g;
@@ -279,7 +285,11 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     if ((rc = ensure(h, h->counter, 64))) return rc;
     BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
     // second stage for the ramp-down (parallel schedule, when the thread-group kernels can take the code)
-    const bool second_stage = h->smem_plan.ok && h->max_iter > 16;
+    // second stage for the ramp-down: the thread-group kernels when they can take the code, else (parallel schedule,
+    // messages beyond shared memory, e.g. n = 10^4) the edge-parallel kernel with its messages in an L2-resident scratch
+    const bool stage2_smem = h->smem_plan.ok && h->smem_plan.serial == (h->schedule == BPB_SERIAL);
+    const bool stage2_edge = !stage2_smem && edge_able(h);
+    const bool second_stage = (stage2_smem || stage2_edge) && h->max_iter > 16 && !std::getenv("BPB_NO_SECOND_STAGE");
     if (second_stage && (rc = ensure(h, h->handoff, (size_t) warps * 32 * sizeof(uint32_t)))) return rc;
     p.iter_cap = second_stage ? 12 : h->max_iter + 1;
     p.handoff_count = (unsigned long long *) h->counter.ptr + 1;
@@ -323,8 +333,10 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     h->last_grid = grid;
     h->last_block = block;
     if (second_stage) {
-        rc = launch_smem(h, d_packed, mwp, batch, d_dec, d_conv, d_iters, d_llr, st, (const uint32_t *) h->handoff.ptr,
-                         (const unsigned long long *) h->counter.ptr + 1);
+        rc = stage2_smem ? launch_smem(h, d_packed, mwp, batch, d_dec, d_conv, d_iters, d_llr, st,
+                                       (const uint32_t *) h->handoff.ptr, (const unsigned long long *) h->counter.ptr + 1)
+                         : launch_edge(h, d_packed, mwp, batch, d_dec, d_conv, d_iters, d_llr, st,
+                                       (const uint32_t *) h->handoff.ptr, (const unsigned long long *) h->counter.ptr + 1);
         if (rc) return rc;
         h->last_family = BPB_KERNEL_STREAM;
         h->last_grid = grid;
@@ -437,6 +449,99 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     h->last_family = BPB_KERNEL_SMEM;
     h->last_grid = (int) grid64;
     h->last_block = block;
+    return BPB_OK;
+}
+
+// ---- edge-parallel family: launch ------------------------------------------------------------------------------
+bool edge_able(const bpb_decoder *h) {
+    return h->schedule == BPB_PARALLEL && h->g.max_row_degree <= 32 && h->g.max_col_degree <= 32 && h->g.nnz > 0;
+}
+
+int launch_edge(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
+                int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
+                const unsigned long long *batch_dev) {
+    const bpb::HostGraph &g = h->g;
+    if (!edge_able(h)) {
+        h->err = "edge-parallel kernel family: parallel schedule and degrees <= 32 only";
+        return BPB_ERR_UNSUPPORTED;
+    }
+    auto pow2_at_least = [](int x) {
+        int p2 = 1;
+        while (p2 < x) p2 <<= 1;
+        return p2;
+    };
+    bpb::EdgeParams p{};
+    p.G = pow2_at_least(std::max(1, g.max_row_degree));
+    p.GV = pow2_at_least(std::max(1, g.max_col_degree));
+    p.MW = (g.m + 31) / 32;
+    const size_t fixed = (size_t) 2 * p.MW * 4 + (size_t) round_up(g.n, 16);
+    const size_t msg_bytes = (size_t) g.nnz * 8;
+    const bool msg_global = msg_bytes + fixed > (size_t) 100 * 1024;  // keep >= 2 CTAs per SM when messages are on chip
+    const bool llr = d_llr != nullptr;
+    bpb::EdgeKernel k = h->method == BPB_MINIMUM_SUM ? bpb::pick_edge_ms(llr, msg_global) : bpb::pick_edge_ps(llr, msg_global);
+    const size_t smem_bytes = fixed + (msg_global ? 0 : msg_bytes);
+    // threads per CTA: one lane per (row, slot) / (column, slot) when that fits; large codes loop
+    int want = std::max(g.m * p.G, g.n * p.GV);
+    int T = msg_global ? 1024 : 512;
+    if (want < T) T = std::max(64, round_up(want, 32));
+    if (const char *ov = std::getenv("BPB_EDGE_THREADS")) {
+        const int t_ov = std::atoi(ov);
+        if (t_ov >= 32 && t_ov % 32 == 0 && t_ov <= 1024) T = t_ov;
+    }
+    BPB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes));
+    int occ = 0;
+    BPB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T, smem_bytes));
+    if (occ < 1) {
+        h->err = "edge kernel does not fit on an SM";
+        return BPB_ERR_UNSUPPORTED;
+    }
+    int64_t grid64 = (int64_t) occ * h->sm_count;
+    if (msg_global) {
+        // keep the message scratch of all resident CTAs inside the L2 (about 100 MB of its 126 MB)
+        const int64_t fit = std::max<int64_t>(1, ((int64_t) 100 << 20) / (int64_t) msg_bytes);
+        grid64 = std::min(grid64, fit);
+    }
+    if (!index_list) grid64 = std::min<int64_t>(grid64, batch);
+    if (grid64 < 1) grid64 = 1;
+    int rc;
+    if ((rc = ensure(h, h->counter, 64))) return rc;
+    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+    if (msg_global && (rc = ensure(h, h->edge_msg, (size_t) grid64 * msg_bytes))) return rc;
+    const uint32_t *blob = (const uint32_t *) h->blob.ptr;
+    p.row_ptr = blob;
+    p.col_idx = p.row_ptr + (g.m + 1);
+    p.col_ptr = p.col_idx + g.nnz;
+    p.csc2csr = p.col_ptr + (g.n + 1);
+    p.row_idx = p.csc2csr + g.nnz;
+    p.prior = reinterpret_cast<const double *>(blob + h->prior_off);
+    p.m = g.m;
+    p.n = g.n;
+    p.nnz = g.nnz;
+    p.max_iter = h->max_iter;
+    p.ms_scaling = h->ms_scaling;
+    p.uniform_prior = h->uniform_prior ? 1 : 0;
+    p.prior0 = h->prior.empty() ? 0.0 : h->prior[0];
+    p.synd_packed = d_packed;
+    p.mwp = mwp;
+    p.batch = batch;
+    p.counter = (unsigned long long *) h->counter.ptr + 2;  // word 2: the second-stage / thread-group queue
+    p.index_list = index_list;
+    p.batch_dev = batch_dev;
+    p.msg_global = (double *) h->edge_msg.ptr;
+    p.out_dec = d_dec;
+    p.out_conv = d_conv;
+    p.out_iters = d_iters;
+    p.out_llr = d_llr;
+    p.llr_last_only = h->llr_last_only ? 1 : 0;
+    if (!index_list) BPB_CUDA(h, cudaEventRecord(h->kev0, st));
+    k<<<(int) grid64, T, smem_bytes, st>>>(p);
+    BPB_CUDA(h, cudaGetLastError());
+    if (!index_list) BPB_CUDA(h, cudaEventRecord(h->kev1, st));
+    h->kernel_timed = true;
+    h->launches += 1;
+    h->last_family = BPB_KERNEL_EDGE;
+    h->last_grid = (int) grid64;
+    h->last_block = T;
     return BPB_OK;
 }
 
@@ -759,9 +864,21 @@ int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, i
     // serial schedule the levelised streaming kernel measured slightly faster (6.5 vs 5.8 M decodes/s at n = 1000,
     // a level has only ~n/30 independent bits), so the on-chip serial kernel serves as its ramp-down second stage
     // and on request (kernel = smem).
-    const bool use_smem = smem_able && (h->kernel_pref == BPB_KERNEL_SMEM ||
-                                        (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
-    if (use_smem)
+    if (h->kernel_pref == BPB_KERNEL_EDGE && !edge_able(h)) {
+        h->err = "kernel family 'edge' serves the parallel schedule with degrees <= 32 only";
+        return BPB_ERR_UNSUPPORTED;
+    }
+    // AUTO, parallel schedule, a batch too small to give every SM a thread group's worth of work: one CTA per
+    // syndrome with a lane per edge has the lower latency (latency table)
+    const bool small_batch = batch <= (int64_t) h->sm_count * 2;
+    const bool use_edge = h->kernel_pref == BPB_KERNEL_EDGE ||
+                          (h->kernel_pref == BPB_KERNEL_AUTO && edge_able(h) && small_batch && !std::getenv("BPB_NO_EDGE_AUTO"));
+    const bool use_smem = !use_edge && smem_able &&
+                          (h->kernel_pref == BPB_KERNEL_SMEM ||
+                           (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
+    if (use_edge)
+        rc = launch_edge(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st, nullptr, nullptr);
+    else if (use_smem)
         rc = launch_smem(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st, nullptr, nullptr);
     else
         rc = launch_stream(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st);

@@ -99,6 +99,7 @@ struct bpb_decoder {
     bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed, smem_tab, handoff;
     bpb::DeviceBuffer osd_llr, osd_fail_llr, osd_fail_idx, osd_count;  // BP+OSD batch path
     bpb::OsdDevicePlan osd_plan;
+    bpb::DeviceBuffer edge_msg;  // edge-parallel family: message scratch of the resident CTAs (large codes)
     bpb::DeviceBuffer mc_thresh, mc_err, mc_syn, mc_dec, mc_conv, mc_its, mc_counts;  // bpb_mc_bsc workspaces
     int osd_location = BPB_OSD_AUTO;  // where OSD-0 runs in the BP+OSD entry points
     bool llr_last_only = false;       // BP+OSD: posterior LLRs are only needed for syndromes that ran max_iter

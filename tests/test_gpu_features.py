@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _bposd(H, p, where, **kw):
-    return BpOsdDecoder(H, error_rate=p, osd_method="osd0", osd_location=where, **kw)
+    chan = dict(error_rate=float(p)) if np.isscalar(p) else dict(error_channel=p)
+    return BpOsdDecoder(H, osd_method="osd0", osd_location=where, **chan, **kw)
 
 
 @pytest.mark.parametrize("case", ["surface13_ps", "surface7_ps_nan", "bb144_ms", "ldpc1000_ms", "hamming_ps", "irregular"])
@@ -24,7 +25,12 @@ def test_device_osd0_equals_host_osd0(case, port_oracle):
     if case == "surface13_ps":
         H, p, B, kw = codes.rotated_surface_code_x(13), 0.05, 20000, dict(max_iter=30, bp_method="ps")
     elif case == "surface7_ps_nan":
-        H, p, B, kw = codes.rotated_surface_code_x(7), 0.1, 20000, dict(max_iter=40, bp_method="ps")
+        # a channel that declares some bits error-free (p = 0: prior +inf) while the sampled errors flip them anyway:
+        # BP cannot converge and the posteriors of the failures contain +-inf and NaN (inf - inf)
+        H, B, kw = codes.rotated_surface_code_x(7), 20000, dict(max_iter=40, bp_method="ps")
+        p = np.full(H.shape[1], 0.1)
+        p[::6] = 0.0
+        p[1::6] = 1.0  # and some certainly flipped (prior -inf): neighbours receive +inf and -inf
     elif case == "bb144_ms":
         H, p, B, kw = codes.bivariate_bicycle_144(), 0.03, 20000, dict(max_iter=50, bp_method="ms", ms_scaling_factor=0.625)
     elif case == "ldpc1000_ms":
@@ -38,8 +44,12 @@ def test_device_osd0_equals_host_osd0(case, port_oracle):
         dense[:, dense.sum(0) == 0] |= (rng.random((40, 1)) < 0.1).astype(np.uint8)
         dense[np.arange(40), np.arange(40)] = 1
         H, p, B, kw = sp.csr_matrix(dense), 0.08, 5000, dict(max_iter=6, bp_method="ms", ms_scaling_factor=0.9)
-    syn = codes.bsc_syndromes(H, p, B, seed=21) if case != "hamming_ps" else \
-        codes.syndromes_of(H, codes.bsc_errors(H.shape[1], p, B, seed=3))
+    if case == "hamming_ps":
+        syn = codes.syndromes_of(H, codes.bsc_errors(H.shape[1], p, B, seed=3))
+    elif case == "surface7_ps_nan":
+        syn = codes.bsc_syndromes(H, 0.1, B, seed=21)
+    else:
+        syn = codes.bsc_syndromes(H, p, B, seed=21)
     dev = _bposd(H, p, "device", **kw)
     host = _bposd(H, p, "host", **kw)
     got = dev.decode_batch(syn, return_bp_decoding=True)
@@ -50,9 +60,10 @@ def test_device_osd0_equals_host_osd0(case, port_oracle):
     assert np.array_equal(dev.converge_batch, host.converge_batch) and np.array_equal(dev.iter_batch, host.iter_batch)
     rows = (got != want).any(axis=1)
     assert not rows.any(), f"{int(rows.sum())} rows differ between device and host OSD-0"
-    assert np.array_equal(codes.syndromes_of(H, got), syn)  # every syndrome is in the image here
+    assert np.array_equal(codes.syndromes_of(H, got), syn)  # every syndrome is in the image here (s = H e)
     # raw BP output kept on request
-    bp = BpDecoder(H, error_rate=p, input_vector_type="syndrome", **kw).decode_batch(syn)
+    chan = dict(error_rate=float(p)) if np.isscalar(p) else dict(error_channel=p)
+    bp = BpDecoder(H, input_vector_type="syndrome", **chan, **kw).decode_batch(syn)
     assert np.array_equal(dev.bp_decoding_batch, bp)
     # and the oracle's BP + OSD-0 restatement on a slice
     sl = slice(0, min(B, 3000))
@@ -62,7 +73,8 @@ def test_device_osd0_equals_host_osd0(case, port_oracle):
         w[~r[1]] = port_oracle.osd0_batch(H, syn[sl][~r[1]], r[3][~r[1]])
     assert np.array_equal(got[sl], w)
     if case == "surface7_ps_nan":
-        assert not np.isfinite(r[3][~r[1]]).all(), "this case is meant to cover non-finite LLRs"
+        bad_llr = r[3][~r[1]]
+        assert np.isnan(bad_llr).any() and np.isinf(bad_llr).any(), "this case is meant to cover non-finite LLRs"
 
 
 def test_device_osd_unavailable_for_large_code():
@@ -167,7 +179,7 @@ def test_monte_carlo_on_device_counts_exactly(case):
         m = BpDecoder(H, error_rate=p, max_iter=50, bp_method="ms", ms_scaling_factor=0.625,
                       input_vector_type="syndrome", devices=[0, 0])
         assert m.monte_carlo_bsc(runs, seed=seed, first_run=first) == want
-        sim = MonteCarloBscSimulation(H, error_rate=p, Decoder=d, target_run_count=runs, seed=seed, device_side=True,
+        sim = MonteCarloBscSimulation(H, error_rate=p, Decoder=d, target_run_count=runs, seed=12345, device_side=True,
                                       tqdm_disable=True)
         res = sim.run()
         assert res["run_count"] == runs and 0 < res["fail_count"] < runs
