@@ -2,7 +2,7 @@
 """bench.py -- syndrome decodes/sec of the batched BP decoder on the BASELINE.json configurations.
 
     python bench.py [--config 1..5] [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--batch B] [--kernel auto|stream|smem|edge]
+                    [--batch B] [--kernel auto|stream|smem|pair|edge]
 
 Default = BASELINE.json configs[1], the one the metric is quoted on: (3,6)-regular LDPC n=1000, min-sum, parallel
 schedule, max_iter=50, ms_scaling_factor=0.625, one batch of 2^20 synthetic BSC(p=0.05) syndromes per step.  A "step"
@@ -279,7 +279,7 @@ def roofline_record(info, alg_bytes, kms, clocks, E, n, m, its_sum, B, conv_frac
             "peak_source": f"derived: 128 B/clk/SM shared-memory crossbar x {sms} SMs x {sm_mhz:.0f} MHz (SM clock "
                            f"sampled during the run); message bytes 4*E*8 per iteration move through shared memory, "
                            f"not HBM",
-            "kernel": {2: "bp_smem_kernel", 3: "bp_edge_kernel"}.get(fam, "?"),
+            "kernel": {2: "bp_smem_kernel", 3: "bp_edge_kernel", 4: "bp_pair_kernel"}.get(fam, "?"),
             "note": "on-chip family: index-table and decision-bit accesses share the same crossbar (about +30 % "
                     "wavefronts) and the kernel is co-limited by instruction issue (profiles/)", **common}
 
@@ -557,7 +557,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--batch", type=int, default=0, help="syndromes per GPU per step (default: the config's)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "stream", "smem", "edge"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "stream", "smem", "pair", "edge"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream-family", action="store_true", help="skip the extra streaming-family measurement")
     ap.add_argument("--no-python-e2e", action="store_true", help="skip the Python-API end-to-end measurements")

@@ -38,8 +38,10 @@ enum { BPB_PRODUCT_SUM = 0, BPB_MINIMUM_SUM = 1 };
 enum { BPB_SERIAL = 0, BPB_PARALLEL = 1 };
 /* ldpc::bp::BpInputType, bp.hpp:34-38 */
 enum { BPB_INPUT_SYNDROME = 0, BPB_INPUT_RECEIVED_VECTOR = 1 };
-/* kernel family: AUTO picks the fastest family that supports the code */
-enum { BPB_KERNEL_AUTO = 0, BPB_KERNEL_STREAM = 1, BPB_KERNEL_SMEM = 2, BPB_KERNEL_EDGE = 3 };
+/* kernel family: AUTO picks the fastest family that supports the code (STREAM: a lane per syndrome, messages in HBM;
+ * SMEM: a thread group per syndrome, messages in shared memory; PAIR: a thread group per two syndromes, double2
+ * messages in shared memory; EDGE: a CTA per syndrome, a lane per edge) */
+enum { BPB_KERNEL_AUTO = 0, BPB_KERNEL_STREAM = 1, BPB_KERNEL_SMEM = 2, BPB_KERNEL_EDGE = 3, BPB_KERNEL_PAIR = 4 };
 /* where OSD-0 runs in the BP+OSD entry points: AUTO = on the device when the code fits (m <= 1024 and the permuted
  * bit matrix fits the shared memory of an SM), else on the host */
 enum { BPB_OSD_AUTO = 0, BPB_OSD_HOST = 1, BPB_OSD_DEVICE = 2 };
@@ -147,6 +149,8 @@ typedef struct {
     int64_t osd_host_solved;      /* syndromes solved by the host elimination so far */
     int64_t osd_host_inconsistent; /* of those (and of bpb_osd0_host calls): syndromes outside the image of H, for
                                       which the result is defined here but differs from the reference's (osd_host.cpp) */
+    int pair_family_available;    /* 1 when the paired on-chip family (two syndromes per thread group) can serve it */
+    int pair_bank_multiplicity;   /* worst lanes-per-bank-quad of a quarter-warp 16-byte message access (1 = none) */
 } bpb_info;
 int bpb_get_info(const bpb_decoder *h, bpb_info *out);
 

@@ -37,6 +37,8 @@ cdef extern from "bp_b200.h":
         int64_t osd_device_solved
         int64_t osd_host_solved
         int64_t osd_host_inconsistent
+        int pair_family_available
+        int pair_bank_multiplicity
     int bpb_create(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *cols, int device,
                    bpb_decoder **out) nogil
     void bpb_destroy(bpb_decoder *h) nogil
@@ -170,4 +172,6 @@ cdef class NativeHandle:
                 "smem_bytes_per_syndrome": inf.smem_bytes_per_syndrome, "stream_iterations": inf.stream_iterations,
                 "stream_handed_off": inf.stream_handed_off,
                 "osd_device_available": inf.osd_device_available, "osd_device_solved": inf.osd_device_solved,
-                "osd_host_solved": inf.osd_host_solved, "osd_host_inconsistent": inf.osd_host_inconsistent}
+                "osd_host_solved": inf.osd_host_solved, "osd_host_inconsistent": inf.osd_host_inconsistent,
+                "pair_family_available": inf.pair_family_available,
+                "pair_bank_multiplicity": inf.pair_bank_multiplicity}

@@ -24,7 +24,7 @@ OK = 0
 PRODUCT_SUM, MINIMUM_SUM = 0, 1          # reference bp.hpp:23-26
 SERIAL, PARALLEL, SERIAL_RELATIVE = 0, 1, 2  # reference bp.hpp:28-32
 INPUT_SYNDROME, INPUT_RECEIVED_VECTOR, INPUT_AUTO = 0, 1, 2  # reference bp.hpp:34-38
-KERNEL_AUTO, KERNEL_STREAM, KERNEL_SMEM, KERNEL_EDGE = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_STREAM, KERNEL_SMEM, KERNEL_EDGE, KERNEL_PAIR = 0, 1, 2, 3, 4
 OSD_AUTO, OSD_HOST, OSD_DEVICE = 0, 1, 2
 
 
@@ -35,7 +35,8 @@ class BpbInfo(C.Structure):
                 ("last_kernel_ms", C.c_double), ("smem_family_available", C.c_int),
                 ("smem_bank_multiplicity", C.c_int), ("smem_bytes_per_syndrome", C.c_int),
                 ("stream_iterations", C.c_int64), ("stream_handed_off", C.c_int64),
-                ("osd_device_available", C.c_int), ("osd_device_solved", C.c_int64), ("osd_host_solved", C.c_int64), ("osd_host_inconsistent", C.c_int64)]
+                ("osd_device_available", C.c_int), ("osd_device_solved", C.c_int64), ("osd_host_solved", C.c_int64), ("osd_host_inconsistent", C.c_int64),
+                ("pair_family_available", C.c_int), ("pair_bank_multiplicity", C.c_int)]
 
 
 EXPORTS = [

@@ -124,7 +124,7 @@ class BpDecoderBase:
             if self._random_serial_schedule:
                 raise NotImplementedError("random_serial_schedule is not implemented on the GPU path")
             kern = {"auto": _capi.KERNEL_AUTO, "stream": _capi.KERNEL_STREAM, "smem": _capi.KERNEL_SMEM,
-                    "edge": _capi.KERNEL_EDGE}[str(self._kernel).lower()]
+                    "edge": _capi.KERNEL_EDGE, "pair": _capi.KERNEL_PAIR}[str(self._kernel).lower()]
             self._native.configure(self._channel, self._max_iter, self._bp_method, self._schedule,
                                    self._ms_scaling_factor, self._serial_schedule_order, kern)
             self._native.set_osd_location(self._osd_location)
@@ -362,7 +362,7 @@ class BpDecoder(BpDecoderBase):
     """Belief propagation decoder for binary linear codes (reference ``BpDecoder``, _bp_decoder.pyx:581-709).
 
     Parameters are the reference's; ``device`` (CUDA ordinal), ``devices`` (list of ordinals: every batch call is split over
-    them inside the library) and ``kernel`` ('auto' | 'stream' | 'smem' | 'edge') are additions.  ``decode`` takes one syndrome (or received vector); ``decode_batch`` takes ``[B, m]``.
+    them inside the library) and ``kernel`` ('auto' | 'stream' | 'smem' | 'pair' | 'edge') are additions.  ``decode`` takes one syndrome (or received vector); ``decode_batch`` takes ``[B, m]``.
     """
 
     def __init__(self, pcm, error_rate: Optional[float] = None, error_channel=None, max_iter: Optional[int] = 0,

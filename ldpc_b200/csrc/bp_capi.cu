@@ -15,6 +15,7 @@
 
 #include "bp_decoder.h"
 #include "bp_edge_params.h"
+#include "bp_pair_params.h"
 #include "bp_smem_params.h"
 #include "bp_stream_params.h"
 
@@ -53,7 +54,7 @@ std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
             &h->packed,   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
             &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1],
             &h->st_bp[0],   &h->st_bp[1],   &h->osd_conv,  &h->mc_thresh, &h->mc_err, &h->mc_syn, &h->mc_dec,
-            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg};
+            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg, &h->pair_tab};
 }
 
 void release(bpb::DeviceBuffer &b) {
@@ -112,6 +113,7 @@ __global__ void xor_received_kernel(uint8_t *__restrict__ dec, const uint8_t *__
 }
 
 using bpb::build_serial_batches;
+using bpb::build_pair_plan;
 using bpb::build_smem_plan;
 using bpb::compute_priors;
 
@@ -218,6 +220,13 @@ int upload_graph(bpb_decoder *h) {
         BPB_CUDA(h, cudaMemcpyAsync(h->smem_tab.ptr, h->smem_plan.blob.data(), h->smem_plan.blob.size(),
                                     cudaMemcpyHostToDevice, h->stream));
     }
+    build_pair_plan(h);
+    if (h->pair_plan.ok) {
+        rc = ensure(h, h->pair_tab, h->pair_plan.blob.size());
+        if (rc) return rc;
+        BPB_CUDA(h, cudaMemcpyAsync(h->pair_tab.ptr, h->pair_plan.blob.data(), h->pair_plan.blob.size(),
+                                    cudaMemcpyHostToDevice, h->stream));
+    }
     BPB_CUDA(h, cudaStreamSynchronize(h->stream));  // the host vector `blob` dies here
     h->graph_dirty = false;
     return BPB_OK;
@@ -236,6 +245,11 @@ StreamKernel pick_stream(int method, int schedule, int dc, int dv, bool reg, boo
 }
 
 int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
+                int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
+                const unsigned long long *batch_dev);
+
+bool pair_able(const bpb_decoder *h);
+int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
                 int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
                 const unsigned long long *batch_dev);
 
@@ -447,6 +461,109 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     h->kernel_timed = true;
     h->launches += 1;
     h->last_family = BPB_KERNEL_SMEM;
+    h->last_grid = (int) grid64;
+    h->last_block = block;
+    return BPB_OK;
+}
+
+// ---- paired on-chip family: launch ------------------------------------------------------------------------------
+bool pair_able(const bpb_decoder *h) { return h->schedule == BPB_PARALLEL && h->pair_plan.ok; }
+
+int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
+                int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
+                const unsigned long long *batch_dev) {
+    const bpb::HostGraph &g = h->g;
+    const bpb::PairPlan &pl = h->pair_plan;
+    const bool llr = d_llr != nullptr;
+    bpb::PairKernel k = nullptr;
+    int maxt = 512;
+    if (const char *ov = std::getenv("BPB_PAIR_CTA_THREADS")) maxt = std::atoi(ov);  // tuning override: 512 | 640 | 768
+    auto pick = [&](int cta) {
+        return h->method == BPB_MINIMUM_SUM
+                   ? bpb::pick_pair_ms(g.max_row_degree, g.max_col_degree, g.regular, llr, cta)
+                   : bpb::pick_pair_ps(g.max_row_degree, g.max_col_degree, g.regular, llr, cta);
+    };
+    if (pair_able(h)) {
+        k = pick(maxt);
+        if (!k) k = pick(maxt = 512);
+    }
+    if (!k) {
+        h->err = "paired on-chip kernel family not available for this code / schedule: " + pl.why;
+        return BPB_ERR_UNSUPPORTED;
+    }
+    const size_t tab = pl.blob.size();
+    int G = (int) (((size_t) h->max_smem_optin - tab) / pl.group_bytes);
+    G = std::min(G, 15);  // named barriers 1..15
+    int T = maxt / G / 32 * 32;
+    if (T < 32) {
+        T = 32;
+        G = maxt / 32;
+    }
+    // a thread per row / two columns
+    const int want = std::max(32, (int) align_up((uint32_t) std::max(g.m, (g.n + 1) / 2), 32));
+    T = std::min(T, std::min(want, 256));
+    if (const char *ov = std::getenv("BPB_PAIR_GROUP_THREADS")) {  // tuning override: threads per group
+        const int t_ov = std::atoi(ov);
+        if (t_ov >= 32 && t_ov % 32 == 0 && t_ov <= maxt) {
+            T = t_ov;
+            G = std::min(G, maxt / T);
+        }
+    }
+    const int block = G * T;
+    const size_t smem_bytes = tab + (size_t) G * pl.group_bytes;
+    BPB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes));
+    int64_t grid64 = std::min<int64_t>(h->sm_count, (batch + 2 * G - 1) / (2 * G));
+    if (grid64 < 1) grid64 = 1;
+    int rc;
+    if ((rc = ensure(h, h->counter, 64))) return rc;
+    // counter words: [0] streaming queue, [1] hand-off count, [2] thread-group queue
+    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+    if (index_list) grid64 = h->sm_count;  // the count lives on the device
+    bpb::PairParams p{};
+    p.tab = (const uint32_t *) h->pair_tab.ptr;
+    p.tab_bytes = (uint32_t) tab;
+    p.off_row_deg = pl.off_row_deg;
+    p.off_col_deg = pl.off_col_deg;
+    p.off_col_row = pl.off_col_row;
+    p.off_row_pos = pl.off_row_pos;
+    p.off_col_pos = pl.off_col_pos;
+    p.off_prior = pl.off_prior;
+    p.group_bytes = pl.group_bytes;
+    p.goff_msg = pl.goff_msg;
+    p.goff_dec = pl.goff_dec;
+    p.goff_syn = pl.goff_syn;
+    p.goff_acc = pl.goff_acc;
+    p.goff_ctl = pl.goff_ctl;
+    p.m = g.m;
+    p.n = g.n;
+    p.M = pl.M;
+    p.N = pl.N;
+    p.MW = (g.m + 31) / 32;
+    p.NW = pl.N / 32;
+    p.groups = G;
+    p.T = T;
+    p.max_iter = h->max_iter;
+    p.ms_scaling = h->ms_scaling;
+    p.uniform_prior = h->uniform_prior ? 1 : 0;
+    p.prior0 = h->prior.empty() ? 0.0 : h->prior[0];
+    p.synd_packed = d_packed;
+    p.mwp = mwp;
+    p.batch = batch;
+    p.counter = (unsigned long long *) h->counter.ptr + 2;
+    p.index_list = index_list;
+    p.batch_dev = batch_dev;
+    p.out_dec = d_dec;
+    p.out_conv = d_conv;
+    p.out_iters = d_iters;
+    p.out_llr = d_llr;
+    p.llr_last_only = h->llr_last_only ? 1 : 0;
+    if (!index_list) BPB_CUDA(h, cudaEventRecord(h->kev0, st));
+    k<<<(int) grid64, block, smem_bytes, st>>>(p);
+    BPB_CUDA(h, cudaGetLastError());
+    if (!index_list) BPB_CUDA(h, cudaEventRecord(h->kev1, st));
+    h->kernel_timed = true;
+    h->launches += 1;
+    h->last_family = BPB_KERNEL_PAIR;
     h->last_grid = (int) grid64;
     h->last_block = block;
     return BPB_OK;
@@ -785,7 +902,7 @@ int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len)
 
 int bpb_set_kernel(bpb_decoder *h, int v) {
     if (!h) return BPB_ERR_ARG;
-    if (v != BPB_KERNEL_AUTO && v != BPB_KERNEL_STREAM && v != BPB_KERNEL_SMEM && v != BPB_KERNEL_EDGE) {
+    if (v != BPB_KERNEL_AUTO && v != BPB_KERNEL_STREAM && v != BPB_KERNEL_SMEM && v != BPB_KERNEL_EDGE && v != BPB_KERNEL_PAIR) {
         h->err = "invalid kernel family";
         return BPB_ERR_ARG;
     }
@@ -873,11 +990,24 @@ int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, i
     const bool small_batch = batch <= (int64_t) h->sm_count * 2;
     const bool use_edge = h->kernel_pref == BPB_KERNEL_EDGE ||
                           (h->kernel_pref == BPB_KERNEL_AUTO && edge_able(h) && small_batch && !std::getenv("BPB_NO_EDGE_AUTO"));
-    const bool use_smem = !use_edge && smem_able &&
+    if (h->kernel_pref == BPB_KERNEL_PAIR && !pair_able(h)) {
+        h->err = "kernel family 'pair' serves the parallel schedule of codes whose messages fit in shared memory twice: " +
+                 h->pair_plan.why;
+        return BPB_ERR_UNSUPPORTED;
+    }
+    // AUTO: the paired kernels (two syndromes per thread group) for min-sum when they can take the code; product-sum
+    // is arithmetic-bound and keeps the one-syndrome groups
+    const bool use_pair = !use_edge && pair_able(h) &&
+                          (h->kernel_pref == BPB_KERNEL_PAIR ||
+                           (h->kernel_pref == BPB_KERNEL_AUTO && h->method == BPB_MINIMUM_SUM &&
+                            !std::getenv("BPB_NO_PAIR_AUTO")));
+    const bool use_smem = !use_edge && !use_pair && smem_able &&
                           (h->kernel_pref == BPB_KERNEL_SMEM ||
                            (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
     if (use_edge)
         rc = launch_edge(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st, nullptr, nullptr);
+    else if (use_pair)
+        rc = launch_pair(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st, nullptr, nullptr);
     else if (use_smem)
         rc = launch_smem(h, d_packed, mwp, batch, d_decoding, d_converged, d_iterations, d_llr, st, nullptr, nullptr);
     else
@@ -975,6 +1105,7 @@ int host_pipeline(bpb_decoder *h, int input_type, const uint8_t *input, int64_t 
     int rc = BPB_OK;
     const int in_w = (input_type == BPB_INPUT_RECEIVED_VECTOR) ? g.n : g.m;
     const bool smem_able = h->smem_plan.ok && (h->kernel_pref == BPB_KERNEL_SMEM || h->kernel_pref == BPB_KERNEL_EDGE ||
+                                               h->kernel_pref == BPB_KERNEL_PAIR ||
                                                (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
     const size_t row_bytes = (size_t) in_w + (size_t) g.n * (bp_decoding ? 2 : 1) + 5 +
                              ((llr || with_osd) ? (size_t) g.n * 8 : 0);
@@ -1385,6 +1516,7 @@ int bpb_get_info(const bpb_decoder *h_, bpb_info *out) {
         if (h->max_smem_optin <= 0) h->max_smem_optin = 232448;
         compute_priors(h);
         build_smem_plan(h);
+        build_pair_plan(h);
         h->graph_dirty = false;
     }
     std::memset(out, 0, sizeof(*out));
@@ -1422,6 +1554,8 @@ int bpb_get_info(const bpb_decoder *h_, bpb_info *out) {
     out->smem_family_available = h->smem_plan.ok ? 1 : 0;
     out->smem_bank_multiplicity = h->smem_plan.max_bank_multiplicity;
     out->smem_bytes_per_syndrome = (int) h->smem_plan.group_bytes;
+    out->pair_family_available = h->pair_plan.ok ? 1 : 0;
+    out->pair_bank_multiplicity = h->pair_plan.max_bank_multiplicity;
     if (h->kernel_timed) {
         // CUDA-event time of the most recent message-update kernel (valid once that launch has finished)
         float ms = 0;

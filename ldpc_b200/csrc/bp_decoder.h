@@ -47,6 +47,18 @@ struct SmemPlan {
     int M = 0, N = 0;
 };
 
+// Shared-memory plan of the paired on-chip kernel family (bp_pair.cuh): two syndromes per thread group, double2 slots.
+struct PairPlan {
+    bool ok = false;
+    std::string why;
+    std::vector<uint8_t> blob;
+    uint32_t off_row_deg = 0, off_col_deg = 0, off_col_row = 0, off_row_pos = 0, off_col_pos = 0, off_prior = 0;
+    int max_bank_multiplicity = 0;  // 1 = both passes conflict-free (lanes of a quarter-warp on different bank quads)
+    int msg_slots = 0;              // length of one group's double2 message array (8 * largest colour class)
+    uint32_t group_bytes = 0, goff_msg = 0, goff_dec = 0, goff_syn = 0, goff_acc = 0, goff_ctl = 0;
+    int M = 0, N = 0;
+};
+
 // Device OSD-0 (osd_device.cu): per-warp shared-memory plan; warps_per_cta == 0 when the code does not fit.
 struct OsdDevicePlan {
     int warps_per_cta = 0;
@@ -75,6 +87,8 @@ namespace bpb {
 void compute_priors(bpb_decoder *h);
 std::vector<uint32_t> build_serial_batches(const HostGraph &g, const std::vector<uint32_t> &order, int sb);
 void build_smem_plan(bpb_decoder *h);
+void build_pair_plan(bpb_decoder *h);
+int place_messages(const HostGraph &g, int lanes_per_phase, std::vector<uint32_t> &slot_of_edge);
 }  // namespace bpb
 
 struct bpb_decoder {
@@ -112,6 +126,8 @@ struct bpb_decoder {
     size_t pin_in_bytes[2] = {0, 0};
     unsigned long long *host_counts = nullptr;  // pinned: failure counts of the two pipeline slots
     bpb::SmemPlan smem_plan;
+    bpb::PairPlan pair_plan;
+    bpb::DeviceBuffer pair_tab;
     // staging for the host API
     bpb::DeviceBuffer st_in[2], st_dec[2], st_conv[2], st_iters[2], st_llr[2], st_bp[2], osd_conv;
     std::vector<bpb_decoder *> children;  // bpb_set_devices: one full decoder per device, this handle only splits

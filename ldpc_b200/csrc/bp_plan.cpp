@@ -52,6 +52,69 @@ std::vector<uint32_t> build_serial_batches(const bpb::HostGraph &g, const std::v
 
 static inline uint32_t align_up(uint32_t x, uint32_t q) { return (x + q - 1) / q * q; }
 
+// Conflict-free message placement.  Every message is written by one thread and read by another: row threads touch
+// it in the check pass (L consecutive rows, same slot k, form one shared-memory phase), column threads in the bit
+// pass (L consecutive columns, same slot).  L = 16 for 8-byte accesses (served per half-warp, conflict-free iff the
+// 16 lanes hit 16 different bank pairs), L = 8 for 16-byte accesses (served per quarter-warp, 8 different bank
+// quads).  Take the bipartite multigraph whose left nodes are the (row group, slot) cells, right nodes the (column
+// group, slot) cells and whose edges are the nonzeros of H: every node has degree <= L, so by Koenig's theorem its
+// edges can be coloured with L colours such that no two edges at a node share a colour.  Colour = bank pair / quad:
+// both passes become conflict-free.  (Alternating-path edge colouring.)  Returns the length of the message array in
+// slots (L * largest colour class); slot_of_edge[CSR edge id] = colour + L * rank inside the colour class.
+int place_messages(const HostGraph &g, int L, std::vector<uint32_t> &slot_of_edge) {
+    const int DCm = g.max_row_degree, DVm = g.max_col_degree;
+    const int n_rc = ((g.m + L - 1) / L) * DCm, n_cc = ((g.n + L - 1) / L) * DVm;
+    std::vector<int> edge_rc((size_t) g.nnz), edge_cc((size_t) g.nnz), colour((size_t) g.nnz, -1);
+    std::vector<int> at_r((size_t) n_rc * L, -1), at_c((size_t) n_cc * L, -1);  // edge using colour q at the node
+    for (int i = 0; i < g.m; i++)
+        for (uint32_t q = g.row_ptr[(size_t) i]; q < g.row_ptr[(size_t) i + 1]; q++)
+            edge_rc[q] = (i / L) * DCm + (int) (q - g.row_ptr[(size_t) i]);
+    for (int j = 0; j < g.n; j++)
+        for (uint32_t q = g.col_ptr[(size_t) j]; q < g.col_ptr[(size_t) j + 1]; q++)
+            edge_cc[g.csc2csr[q]] = (j / L) * DVm + (int) (q - g.col_ptr[(size_t) j]);
+    for (int e = 0; e < g.nnz; e++) {
+        const int u = edge_rc[(size_t) e], v = edge_cc[(size_t) e];
+        int a = 0, b = 0;
+        while (at_r[(size_t) u * L + a] >= 0) a++;  // free at u (exists: degree <= L and e itself uncoloured)
+        while (at_c[(size_t) v * L + b] >= 0) b++;  // free at v
+        if (a != b) {
+            // walk the a/b alternating path that starts at v with colour a and swap a <-> b along it; it cannot
+            // reach u (bipartite, a is free at u), so afterwards a is free at both ends
+            std::vector<int> path;
+            int node = v, want = a;
+            bool on_col_side = true;
+            for (;;) {
+                const int f = on_col_side ? at_c[(size_t) node * L + want] : at_r[(size_t) node * L + want];
+                if (f < 0) break;
+                path.push_back(f);
+                node = on_col_side ? edge_rc[(size_t) f] : edge_cc[(size_t) f];
+                on_col_side = !on_col_side;
+                want = (want == a) ? b : a;
+            }
+            for (int f: path) {
+                at_r[(size_t) edge_rc[(size_t) f] * L + colour[(size_t) f]] = -1;
+                at_c[(size_t) edge_cc[(size_t) f] * L + colour[(size_t) f]] = -1;
+            }
+            for (int f: path) {
+                colour[(size_t) f] = (colour[(size_t) f] == a) ? b : a;
+                at_r[(size_t) edge_rc[(size_t) f] * L + colour[(size_t) f]] = f;
+                at_c[(size_t) edge_cc[(size_t) f] * L + colour[(size_t) f]] = f;
+            }
+        }
+        colour[(size_t) e] = a;
+        at_r[(size_t) u * L + a] = e;
+        at_c[(size_t) v * L + a] = e;
+    }
+    std::vector<int> per_colour((size_t) L, 0);
+    slot_of_edge.assign((size_t) g.nnz, 0u);
+    for (int e = 0; e < g.nnz; e++)
+        slot_of_edge[(size_t) e] = (uint32_t) (colour[(size_t) e] + L * per_colour[(size_t) colour[(size_t) e]]++);
+    int longest = 0;
+    for (int q = 0; q < L; q++) longest = std::max(longest, per_colour[(size_t) q]);
+    return L * longest;
+}
+
+
 void build_smem_plan(bpb_decoder *h) {
     const bpb::HostGraph &g = h->g;
     bpb::SmemPlan &pl = h->smem_plan;
@@ -139,60 +202,10 @@ void build_smem_plan(bpb_decoder *h) {
     uint16_t *col_row = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_row);
     uint16_t *row_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_row_pos);
     uint16_t *col_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_pos);
-    // Message placement.  Every message is written by one thread and read by another: row threads touch it in the
-    // check pass (half-warp = 16 consecutive rows, same slot k), column threads in the bit pass (16 consecutive
-    // columns, same slot).  An 8-byte shared-memory access is served per half-warp and is conflict-free iff the 16
-    // lanes hit 16 different bank pairs.  Take the bipartite multigraph whose left nodes are the (row group, slot)
-    // cells, right nodes the (column group, slot) cells and whose edges are the nonzeros of H: every node has degree
-    // <= 16, so by Koenig's theorem its edges can be coloured with 16 colours such that no two edges at a node share
-    // a colour.  Colour = bank pair: both passes become conflict-free.  (Alternating-path edge colouring below.)
-    const int n_rc = ((g.m + 15) / 16) * DCm, n_cc = ((g.n + 15) / 16) * DVm;
-    std::vector<int> edge_rc((size_t) g.nnz), edge_cc((size_t) g.nnz), colour((size_t) g.nnz, -1);
-    std::vector<int> at_r((size_t) n_rc * 16, -1), at_c((size_t) n_cc * 16, -1);  // edge using colour q at the node
-    for (int i = 0; i < g.m; i++)
-        for (uint32_t q = g.row_ptr[(size_t) i]; q < g.row_ptr[(size_t) i + 1]; q++)
-            edge_rc[q] = (i / 16) * DCm + (int) (q - g.row_ptr[(size_t) i]);
-    for (int j = 0; j < g.n; j++)
-        for (uint32_t q = g.col_ptr[(size_t) j]; q < g.col_ptr[(size_t) j + 1]; q++)
-            edge_cc[g.csc2csr[q]] = (j / 16) * DVm + (int) (q - g.col_ptr[(size_t) j]);
-    for (int e = 0; e < g.nnz; e++) {
-        const int u = edge_rc[(size_t) e], v = edge_cc[(size_t) e];
-        int a = 0, b = 0;
-        while (at_r[(size_t) u * 16 + a] >= 0) a++;  // free at u (exists: degree <= 16 and e itself uncoloured)
-        while (at_c[(size_t) v * 16 + b] >= 0) b++;  // free at v
-        if (a != b) {
-            // walk the a/b alternating path that starts at v with colour a and swap a <-> b along it; it cannot
-            // reach u (bipartite, a is free at u), so afterwards a is free at both ends
-            std::vector<int> path;
-            int node = v, want = a;
-            bool on_col_side = true;
-            for (;;) {
-                const int f = on_col_side ? at_c[(size_t) node * 16 + want] : at_r[(size_t) node * 16 + want];
-                if (f < 0) break;
-                path.push_back(f);
-                node = on_col_side ? edge_rc[(size_t) f] : edge_cc[(size_t) f];
-                on_col_side = !on_col_side;
-                want = (want == a) ? b : a;
-            }
-            for (int f: path) {
-                at_r[(size_t) edge_rc[(size_t) f] * 16 + colour[(size_t) f]] = -1;
-                at_c[(size_t) edge_cc[(size_t) f] * 16 + colour[(size_t) f]] = -1;
-            }
-            for (int f: path) {
-                colour[(size_t) f] = (colour[(size_t) f] == a) ? b : a;
-                at_r[(size_t) edge_rc[(size_t) f] * 16 + colour[(size_t) f]] = f;
-                at_c[(size_t) edge_cc[(size_t) f] * 16 + colour[(size_t) f]] = f;
-            }
-        }
-        colour[(size_t) e] = a;
-        at_r[(size_t) u * 16 + a] = e;
-        at_c[(size_t) v * 16 + a] = e;
-    }
-    int per_colour[16] = {0};
-    std::vector<uint32_t> slot_of_edge((size_t) g.nnz);
-    for (int e = 0; e < g.nnz; e++) slot_of_edge[(size_t) e] = (uint32_t) (colour[(size_t) e] + 16 * per_colour[colour[(size_t) e]]++);
-    int longest = 0;
-    for (int q = 0; q < 16; q++) longest = std::max(longest, per_colour[q]);
+    // Message placement: conflict-free in both passes by edge colouring (place_messages above), 16 lanes per
+    // shared-memory phase for 8-byte accesses.
+    std::vector<uint32_t> slot_of_edge;
+    const int longest = place_messages(g, 16, slot_of_edge) / 16;
     pl.msg_doubles = 16 * longest;
     if (pl.msg_doubles > 65535) {
         pl.why = "message positions do not fit 16-bit indices";
@@ -252,6 +265,104 @@ void build_smem_plan(bpb_decoder *h) {
     pl.group_bytes = align_up(go, 16);
     if ((size_t) off + pl.group_bytes > (size_t) h->max_smem_optin) {
         pl.why = "one syndrome's messages do not fit in shared memory";
+        return;
+    }
+    pl.ok = true;
+}
+
+// Tables of the paired on-chip family (bp_pair.cuh): parallel schedule only, double2 message slots placed by an
+// 8-colouring (one colour per bank quad, 8 lanes per 16-byte shared-memory phase).
+void build_pair_plan(bpb_decoder *h) {
+    const bpb::HostGraph &g = h->g;
+    bpb::PairPlan &pl = h->pair_plan;
+    pl = bpb::PairPlan();
+    const int DCm = g.max_row_degree, DVm = g.max_col_degree;
+    const int M = (int) align_up((uint32_t) g.m, 32), N = (int) align_up((uint32_t) g.n, 32);
+    if (DCm > 32 || DVm > 16 || (DCm > 8 && DVm > 4)) {
+        pl.why = "degrees beyond the paired kernels' buckets";
+        return;
+    }
+    if (DCm < 1 || g.n > 65535 || g.m > 65535) {
+        pl.why = "row / column indices do not fit 16 bits";
+        return;
+    }
+    std::vector<uint32_t> slot_of_edge;
+    pl.msg_slots = place_messages(g, 8, slot_of_edge);
+    if (pl.msg_slots > 65535) {
+        pl.why = "message positions do not fit 16-bit indices";
+        return;
+    }
+    pl.M = M;
+    pl.N = N;
+    const int DCp = (DCm + 1) / 2, DVp = (DVm + 1) / 2;
+    uint32_t off = 0;
+    pl.off_row_deg = off;
+    off += (uint32_t) M;
+    pl.off_col_deg = off;
+    off += (uint32_t) N;
+    pl.off_col_row = off;
+    off += 4u * (uint32_t) (DVp * N);
+    pl.off_row_pos = off;
+    off += 4u * (uint32_t) (DCp * M);
+    pl.off_col_pos = off;
+    off += 4u * (uint32_t) (DVp * N);
+    off = align_up(off, 8);
+    pl.off_prior = off;
+    if (!h->uniform_prior) off += 8u * (uint32_t) g.n;
+    off = align_up(off, 16);
+    pl.blob.assign(off, 0);
+    uint8_t *row_deg = pl.blob.data() + pl.off_row_deg;
+    uint8_t *col_deg = pl.blob.data() + pl.off_col_deg;
+    uint16_t *col_row = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_row);
+    uint16_t *row_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_row_pos);
+    uint16_t *col_pos = reinterpret_cast<uint16_t *>(pl.blob.data() + pl.off_col_pos);
+    for (int i = 0; i < g.m; i++) {
+        const uint32_t b = g.row_ptr[(size_t) i], e = g.row_ptr[(size_t) i + 1];
+        row_deg[i] = (uint8_t) (e - b);
+        for (uint32_t q = b; q < e; q++) {
+            const uint32_t k = q - b;
+            row_pos[2 * ((size_t) (k / 2) * M + i) + (k & 1)] = (uint16_t) slot_of_edge[q];
+        }
+    }
+    for (int j = 0; j < g.n; j++) {
+        const uint32_t b = g.col_ptr[(size_t) j], e = g.col_ptr[(size_t) j + 1];
+        col_deg[j] = (uint8_t) (e - b);
+        for (uint32_t q = b; q < e; q++) {
+            col_pos[2 * ((size_t) ((q - b) / 2) * N + j) + ((q - b) & 1)] = (uint16_t) slot_of_edge[g.csc2csr[q]];
+            col_row[2 * ((size_t) ((q - b) / 2) * N + j) + ((q - b) & 1)] = (uint16_t) g.row_idx[q];
+        }
+    }
+    // verify: largest number of lanes of one quarter-warp access that share a bank quad (1 = conflict-free)
+    for (int pass = 0; pass < 2; pass++) {
+        const int items = pass == 0 ? g.m : g.n, stride = pass == 0 ? M : N, slots = pass == 0 ? DCm : DVm;
+        const uint16_t *tab = pass == 0 ? row_pos : col_pos;
+        const uint8_t *deg = pass == 0 ? row_deg : col_deg;
+        for (int base = 0; base < items; base += 8)
+            for (int k = 0; k < slots; k++) {
+                int cnt[8] = {0};
+                for (int x = base; x < std::min(items, base + 8); x++)
+                    if (k < deg[x])
+                        pl.max_bank_multiplicity = std::max(
+                            pl.max_bank_multiplicity, ++cnt[tab[2 * ((size_t) (k / 2) * stride + x) + (k & 1)] & 7]);
+            }
+    }
+    if (!h->uniform_prior) std::memcpy(pl.blob.data() + pl.off_prior, h->prior.data(), 8 * (size_t) g.n);
+    const uint32_t MW = (uint32_t) ((g.m + 31) / 32);
+    uint32_t go = 0;
+    pl.goff_msg = go;
+    go += 16u * (uint32_t) pl.msg_slots;
+    pl.goff_dec = go;
+    go += 2u * (uint32_t) N / 8;  // one bit per column, two syndromes
+    pl.goff_syn = go;
+    go += 2u * 4u * MW;           // two packed syndromes
+    pl.goff_acc = go;
+    go += 2u * 2u * 4u * MW;      // candidate accumulators: two buffers x two syndromes
+    go = align_up(go, 8);
+    pl.goff_ctl = go;
+    go += 16;
+    pl.group_bytes = align_up(go, 16);
+    if ((size_t) off + pl.group_bytes > (size_t) h->max_smem_optin) {
+        pl.why = "two syndromes' messages do not fit in shared memory";
         return;
     }
     pl.ok = true;

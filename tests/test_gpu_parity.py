@@ -10,7 +10,7 @@ from util import assert_same_decode
 pytestmark = pytest.mark.gpu
 
 
-FAMILIES = ["stream", "smem", "edge"]  # "edge" serves the parallel schedule only
+FAMILIES = ["stream", "smem", "pair", "edge"]  # "pair" and "edge" serve the parallel schedule only
 
 
 def _decode_gpu(H, syn, p, kernel="auto", **kw):
@@ -32,8 +32,8 @@ def H1000():
 def test_regular_n1000(port_oracle, H1000, method, schedule, ms_scaling, kernel):
     if method == "ps" and ms_scaling != 0.625:
         pytest.skip("ms_scaling_factor is unused by product_sum")
-    if kernel == "edge" and schedule == "serial":
-        pytest.skip("the edge-parallel family serves the parallel schedule")
+    if kernel in ("edge", "pair") and schedule == "serial":
+        pytest.skip("the edge-parallel and paired families serve the parallel schedule")
     B = 1536 if method == "ms" else 512
     syn = np.concatenate([codes.bsc_syndromes(H1000, 0.05, B, seed=7),
                           codes.bsc_syndromes(H1000, 0.09, B // 8, seed=8)])  # the second part mostly fails
@@ -54,6 +54,8 @@ def test_surface_d13_product_sum(port_oracle, kernel):
 
 @pytest.mark.parametrize("kernel", FAMILIES)
 def test_hamming5_readme_config(port_oracle, kernel):
+    if kernel == "pair":
+        pytest.skip("row degree 16 with column degree 5 is beyond the paired family's buckets")
     H = codes.hamming_code(5)
     rng = np.random.default_rng(0)
     syn = rng.integers(0, 2, size=(100, 5)).astype(np.uint8)
@@ -79,8 +81,8 @@ def test_nonuniform_channel_with_certain_bits(port_oracle, method, kernel):
 
 @pytest.mark.parametrize("kernel", FAMILIES)
 def test_custom_serial_order(port_oracle, kernel):
-    if kernel == "edge":
-        pytest.skip("the edge-parallel family serves the parallel schedule")
+    if kernel in ("edge", "pair"):
+        pytest.skip("the edge-parallel and paired families serve the parallel schedule")
     H = codes.regular_ldpc(200, 3, 6, seed=2)
     order = np.random.default_rng(4).permutation(200)
     syn = codes.bsc_syndromes(H, 0.06, 700, seed=9)
@@ -95,6 +97,8 @@ def test_custom_serial_order(port_oracle, kernel):
 def test_irregular_degrees(port_oracle, kernel):
     """Row degrees 1..~12 and column degrees 1..~9: exercises the larger degree buckets and degree-1 rows
     (magnitude DBL_MAX * alpha)."""
+    if kernel == "pair":
+        pytest.skip("degrees (12, 9) are beyond the paired family's buckets")
     rng = np.random.default_rng(21)
     m, n = 60, 90
     dense = (rng.random((m, n)) < 0.07).astype(np.uint8)
@@ -106,7 +110,7 @@ def test_irregular_degrees(port_oracle, kernel):
     H = sp.csr_matrix(dense)
     syn = codes.syndromes_of(H, err)
     for method, sched in (("ms", "parallel"), ("ps", "parallel"), ("ms", "serial"), ("ps", "serial")):
-        if kernel == "edge" and sched == "serial":
+        if kernel in ("edge", "pair") and sched == "serial":
             continue
         kw = dict(max_iter=15, bp_method=method, schedule=sched, ms_scaling_factor=0.625)
         want = port_oracle.decode_batch(H, syn, 0.04, **kw)
@@ -175,8 +179,11 @@ def test_golden_fixtures_from_reference(kernel):
     for path in paths:
         z = np.load(path, allow_pickle=False)
         H = sp.csr_matrix((np.ones(z["rows"].size, np.uint8), (z["rows"], z["cols"])), shape=tuple(z["shape"]))
-        if kernel == "edge" and str(z["schedule"]) == "serial":
+        if kernel in ("edge", "pair") and str(z["schedule"]) == "serial":
             continue
+        dc, dv = int(np.diff(H.indptr).max()), int(np.diff(H.tocsc().indptr).max())
+        if kernel == "pair" and dc > 8 and dv > 4:
+            continue  # beyond the paired family's degree buckets (hamming_code(5): 16 x 5)
         kw = dict(max_iter=int(z["max_iter"]), bp_method=str(z["bp_method"]), schedule=str(z["schedule"]),
                   ms_scaling_factor=float(z["ms_scaling_factor"]))
         got = _decode_gpu(H, z["syndromes"], z["channel"], kernel=kernel, **kw)

@@ -20,7 +20,7 @@ def _same(got_dec, d, want, what):
     assert np.array_equal(d.iter_batch, want[2]), f"{what}: iteration counts differ"
 
 
-@pytest.mark.parametrize("kernel", ["smem", "stream", "edge"])
+@pytest.mark.parametrize("kernel", ["smem", "pair", "stream", "edge"])
 def test_config2_n1000_minsum_2p17(kernel):
     """BASELINE config 2 on 2^17 syndromes (seed 7, the first 2^17 of the 2^20 workload), every kernel family."""
     H = codes.regular_ldpc(1000, 3, 6, seed=1)
