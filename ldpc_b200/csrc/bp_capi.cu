@@ -467,7 +467,36 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
 }
 
 // ---- paired on-chip family: launch ------------------------------------------------------------------------------
-bool pair_able(const bpb_decoder *h) { return h->schedule == BPB_PARALLEL && h->pair_plan.ok; }
+// Thread groups per CTA and threads per group for a CTA of `maxt` threads.  Every thread keeps the decisions of its
+// own columns in one register, two bits per column: a group must cover the columns in at most 16 rounds.
+bool pair_geometry(const bpb_decoder *h, int maxt, int &G, int &T) {
+    const bpb::PairPlan &pl = h->pair_plan;
+    const bpb::HostGraph &g = h->g;
+    if (!pl.ok || pl.blob.size() + pl.group_bytes > (size_t) h->max_smem_optin) return false;
+    G = (int) (((size_t) h->max_smem_optin - pl.blob.size()) / pl.group_bytes);
+    G = std::min(G, 15);  // named barriers 1..15
+    T = maxt / G / 32 * 32;
+    if (T < 32) {
+        T = 32;
+        G = maxt / 32;
+    }
+    // a thread per row / two columns is enough
+    const int want = std::max(32, (int) align_up((uint32_t) std::max(g.m, (g.n + 1) / 2), 32));
+    T = std::min(T, want);
+    if (const char *ov = std::getenv("BPB_PAIR_GROUP_THREADS")) {  // tuning override: threads per group
+        const int t_ov = std::atoi(ov);
+        if (t_ov >= 32 && t_ov % 32 == 0 && t_ov <= maxt) {
+            T = t_ov;
+            G = std::min(G, maxt / T);
+        }
+    }
+    return (g.n + T - 1) / T <= 16;
+}
+
+bool pair_able(const bpb_decoder *h) {
+    int G, T;
+    return h->schedule == BPB_PARALLEL && h->pair_plan.ok && pair_geometry(h, 512, G, T);
+}
 
 int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch, uint8_t *d_dec, uint8_t *d_conv,
                 int32_t *d_iters, double *d_llr, cudaStream_t st, const uint32_t *index_list,
@@ -476,7 +505,7 @@ int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     const bpb::PairPlan &pl = h->pair_plan;
     const bool llr = d_llr != nullptr;
     bpb::PairKernel k = nullptr;
-    int maxt = 512;
+    int maxt = 512, G = 0, T = 0;
     if (const char *ov = std::getenv("BPB_PAIR_CTA_THREADS")) maxt = std::atoi(ov);  // tuning override: 512 | 640 | 768
     auto pick = [&](int cta) {
         return h->method == BPB_MINIMUM_SUM
@@ -485,30 +514,13 @@ int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     };
     if (pair_able(h)) {
         k = pick(maxt);
-        if (!k) k = pick(maxt = 512);
+        if (!k || !pair_geometry(h, maxt, G, T)) k = pick(maxt = 512);
     }
-    if (!k) {
+    if (!k || !pair_geometry(h, maxt, G, T)) {
         h->err = "paired on-chip kernel family not available for this code / schedule: " + pl.why;
         return BPB_ERR_UNSUPPORTED;
     }
     const size_t tab = pl.blob.size();
-    int G = (int) (((size_t) h->max_smem_optin - tab) / pl.group_bytes);
-    G = std::min(G, 15);  // named barriers 1..15
-    int T = maxt / G / 32 * 32;
-    if (T < 32) {
-        T = 32;
-        G = maxt / 32;
-    }
-    // a thread per row / two columns
-    const int want = std::max(32, (int) align_up((uint32_t) std::max(g.m, (g.n + 1) / 2), 32));
-    T = std::min(T, std::min(want, 256));
-    if (const char *ov = std::getenv("BPB_PAIR_GROUP_THREADS")) {  // tuning override: threads per group
-        const int t_ov = std::atoi(ov);
-        if (t_ov >= 32 && t_ov % 32 == 0 && t_ov <= maxt) {
-            T = t_ov;
-            G = std::min(G, maxt / T);
-        }
-    }
     const int block = G * T;
     const size_t smem_bytes = tab + (size_t) G * pl.group_bytes;
     BPB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes));
@@ -530,7 +542,6 @@ int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.off_prior = pl.off_prior;
     p.group_bytes = pl.group_bytes;
     p.goff_msg = pl.goff_msg;
-    p.goff_dec = pl.goff_dec;
     p.goff_syn = pl.goff_syn;
     p.goff_acc = pl.goff_acc;
     p.goff_ctl = pl.goff_ctl;
@@ -539,7 +550,6 @@ int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.M = pl.M;
     p.N = pl.N;
     p.MW = (g.m + 31) / 32;
-    p.NW = pl.N / 32;
     p.groups = G;
     p.T = T;
     p.max_iter = h->max_iter;

@@ -55,7 +55,7 @@ struct PairPlan {
     uint32_t off_row_deg = 0, off_col_deg = 0, off_col_row = 0, off_row_pos = 0, off_col_pos = 0, off_prior = 0;
     int max_bank_multiplicity = 0;  // 1 = both passes conflict-free (lanes of a quarter-warp on different bank quads)
     int msg_slots = 0;              // length of one group's double2 message array (8 * largest colour class)
-    uint32_t group_bytes = 0, goff_msg = 0, goff_dec = 0, goff_syn = 0, goff_acc = 0, goff_ctl = 0;
+    uint32_t group_bytes = 0, goff_msg = 0, goff_syn = 0, goff_acc = 0, goff_ctl = 0;
     int M = 0, N = 0;
 };
 

@@ -20,8 +20,12 @@
 // incidence graph (bp_plan.cpp: place_messages with L = 8), colour = bank quad, so both passes are conflict-free.
 //
 // Barriers.  Two per iteration (check | bit | next check): after the bit pass every warp reads the candidate-syndrome
-// accumulator words itself and votes with __any_sync, so no third barrier is needed; the accumulator is
-// double-buffered by iteration parity so that the next iteration's reset cannot overtake a slower warp's read.
+// accumulator words itself and votes with __any_sync, so no third barrier is needed.
+//
+// Candidate syndrome and decisions.  Hard decisions stay in registers (each thread owns its columns), and the
+// accumulator  syndrome ^ H x  is kept up to date incrementally: a column XORs its checks in only when its decision
+// flips (few do after the first iterations), which is the reference's candidate_syndrome (bp.hpp:290-300) by
+// linearity.  Converged <=> all accumulator words are zero.
 #pragma once
 #include "bp_pair_params.h"
 #include "bp_smem.cuh"
@@ -62,6 +66,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
     const int lane = t & 31;
     const int bar = g + 1;  // named barrier of this group (0 is the CTA-wide one used above)
     const int m = p.m, n = p.n, M = p.M, N = p.N, MW = p.MW;
+    constexpr int DCp = (DC + 1) / 2, DVp = (DV + 1) / 2;
     const uint8_t *row_deg = sm + p.off_row_deg;
     const uint8_t *col_deg = sm + p.off_col_deg;
     // 16-bit tables, slots (2q, 2q+1) of one row / column packed in the 32-bit word tab[q*stride + x]
@@ -71,17 +76,21 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
     const double *prior = reinterpret_cast<const double *>(sm + p.off_prior);
     uint8_t *garea = sm + p.tab_bytes + (size_t) g * p.group_bytes;
     // per-syndrome words are interleaved {A, B}: one 64-bit access serves both halves of the pair
-    const uint32_t msg_s = smem_addr(garea + p.goff_msg);            // double2 slots: .x syndrome A, .y syndrome B
-    uint2 *dec = reinterpret_cast<uint2 *>(garea + p.goff_dec);      // hard decisions [NW]{A, B}, one bit per column
-    uint2 *synw = reinterpret_cast<uint2 *>(garea + p.goff_syn);     // packed syndromes [MW]{A, B}
-    uint2 *accb = reinterpret_cast<uint2 *>(garea + p.goff_acc);     // candidate ^ syndrome, [2 buffers][MW]{A, B}
+    const uint32_t msg_s = smem_addr(garea + p.goff_msg);         // double2 slots: .x syndrome A, .y syndrome B
+    uint2 *synw = reinterpret_cast<uint2 *>(garea + p.goff_syn);  // packed syndromes [MW]{A, B}
+    uint2 *acc = reinterpret_cast<uint2 *>(garea + p.goff_acc);   // candidate ^ syndrome [MW]{A, B}
+    const uint32_t acc_s = smem_addr(acc);
     volatile long long *ctl = reinterpret_cast<volatile long long *>(garea + p.goff_ctl);
 
     const long long limit = p.batch_dev ? (long long) *p.batch_dev : p.batch;
     long long idx0 = -1, idx1 = -1;  // batch index each half is decoding, -1 = idle
     int it0 = 0, it1 = 0;
     bool need0 = true, need1 = true;  // the half wants a syndrome from the queue (group-uniform)
-    int par = 0;
+    // Hard decisions of this thread's columns j = r*T + t, two bits per round r: bit 2r = syndrome A, 2r+1 = B (the
+    // host guarantees at most 16 rounds).  The candidate syndrome is maintained incrementally: the accumulator starts
+    // as the syndrome, and a column XORs its checks in (bp.hpp:290-294) only when its decision FLIPS, so that
+    // acc == syndrome ^ H x at the end of every bit pass.
+    uint32_t xm = 0;
     for (;;) {
         if (need0 || need1) {
             if (t == 0) {
@@ -106,14 +115,16 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
             const bool f0 = need0 && idx0 >= 0, f1 = need1 && idx1 >= 0;
             need0 = need1 = false;
             if (idx0 < 0 && idx1 < 0) break;
-            // syndrome bits and initialise_log_domain_bp (bp.hpp:147-157) for the fresh halves
+            // syndrome bits, x = 0, and initialise_log_domain_bp (bp.hpp:147-157) for the fresh halves
             if (f0) {
                 const uint32_t *srow = p.synd_packed + idx0 * p.mwp;
-                for (int w = t; w < MW; w += T) synw[w].x = __ldg(srow + w);
+                for (int w = t; w < MW; w += T) acc[w].x = synw[w].x = __ldg(srow + w);
+                xm &= 0xaaaaaaaau;
             }
             if (f1) {
                 const uint32_t *srow = p.synd_packed + idx1 * p.mwp;
-                for (int w = t; w < MW; w += T) synw[w].y = __ldg(srow + w);
+                for (int w = t; w < MW; w += T) acc[w].y = synw[w].y = __ldg(srow + w);
+                xm &= 0x55555555u;
             }
             if (f0 || f1) {
                 for (int j = t; j < n; j += T) {
@@ -131,53 +142,62 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
         ++it0;
         ++it1;
         const double alpha0 = ms_alpha(p.ms_scaling, it0), alpha1 = ms_alpha(p.ms_scaling, it1);
-        uint2 *acc = accb + par * MW;
-        const uint32_t acc_s = smem_addr(acc);
-        par ^= 1;
-        for (int w = t; w < MW; w += T) acc[w] = synw[w];  // candidate ^ syndrome, must end up all zero
-        // ---- check -> bit, one thread per row (bp.hpp:201-273) ----
-        for (int i = t; i < m; i += T) {
-            const int deg = UNI ? DC : row_deg[i];
-            uint32_t rp[DC];
-            double b0[DC], b1[DC], c0[DC], c1[DC];
+        // ---- check -> bit, one thread per row (bp.hpp:201-273); the table words of the next row are fetched while
+        // this one is computed ----
+        {
+            uint32_t wn[DCp];
 #pragma unroll
-            for (int q = 0; q < (DC + 1) / 2; ++q) {
-                const uint32_t w = (2 * q < deg) ? row_pos[q * M + i] : 0u;
-                rp[2 * q] = slot_addr(msg_s, w, 0);
-                if (2 * q + 1 < DC) rp[2 * q + 1] = slot_addr(msg_s, w, 1);
+            for (int q = 0; q < DCp; ++q) wn[q] = (t < m) ? row_pos[q * M + t] : 0u;
+            for (int i = t; i < m; i += T) {
+                const int deg = UNI ? DC : row_deg[i];
+                uint32_t rp[DC];
+                double b0[DC], b1[DC], c0[DC], c1[DC];
+#pragma unroll
+                for (int q = 0; q < DCp; ++q) {
+                    rp[2 * q] = slot_addr(msg_s, wn[q], 0);
+                    if (2 * q + 1 < DC) rp[2 * q + 1] = slot_addr(msg_s, wn[q], 1);
+                }
+#pragma unroll
+                for (int k = 0; k < DC; ++k) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (k < deg) v = lds128(rp[k]);
+                    b0[k] = v.x;
+                    b1[k] = v.y;
+                }
+                const uint2 sw = synw[i >> 5];
+                if (i + T < m) {
+#pragma unroll
+                    for (int q = 0; q < DCp; ++q) wn[q] = row_pos[q * M + i + T];
+                }
+                const uint32_t sh = (uint32_t) i & 31u;
+                check_node_update<METHOD, DC>(b0, deg, (sw.x >> sh) & 1u, alpha0, c0);
+                check_node_update<METHOD, DC>(b1, deg, (sw.y >> sh) & 1u, alpha1, c1);
+#pragma unroll
+                for (int k = 0; k < DC; ++k)
+                    if (k < deg) sts128(rp[k], c0[k], c1[k]);
             }
-            const uint2 sw = synw[i >> 5];
-#pragma unroll
-            for (int k = 0; k < DC; ++k) {
-                double2 v = make_double2(0.0, 0.0);
-                if (k < deg) v = lds128(rp[k]);
-                b0[k] = v.x;
-                b1[k] = v.y;
-            }
-            const uint32_t sh = (uint32_t) i & 31u;
-            check_node_update<METHOD, DC>(b0, deg, (sw.x >> sh) & 1u, alpha0, c0);
-            check_node_update<METHOD, DC>(b1, deg, (sw.y >> sh) & 1u, alpha1, c1);
-#pragma unroll
-            for (int k = 0; k < DC; ++k)
-                if (k < deg) sts128(rp[k], c0[k], c1[k]);
         }
         group_sync(bar, T);
         // ---- posterior, decision, bit -> check, one thread per column (bp.hpp:276-318) ----
         const bool llr0_on = LLR && idx0 >= 0 && (!p.llr_last_only || it0 == p.max_iter);
         const bool llr1_on = LLR && idx1 >= 0 && (!p.llr_last_only || it1 == p.max_iter);
-        for (int j0 = 0; j0 < N; j0 += T) {  // N is a multiple of 32: whole warps are in or out
-            const int j = j0 + t;
-            bool x0 = false, x1 = false;
-            if (j < n) {
+        {
+            uint32_t wn[DVp], crn[DVp];
+#pragma unroll
+            for (int q = 0; q < DVp; ++q) {
+                wn[q] = (t < n) ? col_pos[q * N + t] : 0u;
+                crn[q] = (t < n) ? col_row[q * N + t] : 0u;
+            }
+            int rounds = 0;
+            for (int j = t; j < n; j += T, ++rounds) {
                 const int deg = UNI ? DV : col_deg[j];
-                uint32_t pos[DV], cr[(DV + 1) / 2];
+                uint32_t pos[DV], cr[DVp];
                 double c0[DV], c1[DV];
 #pragma unroll
-                for (int q = 0; q < (DV + 1) / 2; ++q) {
-                    const uint32_t w = (2 * q < deg) ? col_pos[q * N + j] : 0u;
-                    cr[q] = (2 * q < deg) ? col_row[q * N + j] : 0u;
-                    pos[2 * q] = slot_addr(msg_s, w, 0);
-                    if (2 * q + 1 < DV) pos[2 * q + 1] = slot_addr(msg_s, w, 1);
+                for (int q = 0; q < DVp; ++q) {
+                    cr[q] = crn[q];
+                    pos[2 * q] = slot_addr(msg_s, wn[q], 0);
+                    if (2 * q + 1 < DV) pos[2 * q + 1] = slot_addr(msg_s, wn[q], 1);
                 }
 #pragma unroll
                 for (int k = 0; k < DV; ++k) {
@@ -186,37 +206,41 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
                     c0[k] = v.x;
                     c1[k] = v.y;
                 }
+                if (j + T < n) {
+#pragma unroll
+                    for (int q = 0; q < DVp; ++q) {
+                        wn[q] = col_pos[q * N + j + T];
+                        crn[q] = col_row[q * N + j + T];
+                    }
+                }
                 const double pr = p.uniform_prior ? p.prior0 : prior[j];
                 const double llr0 = bit_node_update<DV>(c0, deg, pr);
                 const double llr1 = bit_node_update<DV>(c1, deg, pr);
 #pragma unroll
                 for (int k = 0; k < DV; ++k)
                     if (k < deg) sts128(pos[k], c0[k], c1[k]);
-                x0 = (llr0 <= 0);
-                x1 = (llr1 <= 0);
                 if (LLR) {
                     if (llr0_on) p.out_llr[idx0 * n + j] = llr0;
                     if (llr1_on) p.out_llr[idx1 * n + j] = llr1;
                 }
-                // bp.hpp:290-294: a decided-1 bit flips the candidate syndrome of its checks.  One branch for the pair
-                // (about one lane in ten takes it); inside it the half that decided 0 XORs a zero.
-                if (x0 || x1) {
+                // decisions of this round sit in the two low bits of xm; rotate to the next round afterwards
+                const uint32_t now = ((llr0 <= 0) ? 1u : 0u) | ((llr1 <= 0) ? 2u : 0u);
+                const uint32_t flip = (xm ^ now) & 3u;
+                xm ^= flip;
+                if (flip) {
 #pragma unroll
                     for (int k = 0; k < DV; ++k)
                         if (k < deg) {
                             const uint32_t r = __byte_perm(cr[k >> 1], 0u, (k & 1) ? 0x4432u : 0x4410u);
                             const uint32_t bit = 1u << (r & 31u);
                             const uint32_t a = acc_s + (r >> 5) * 8u;
-                            smem_xor(a, x0 ? bit : 0u);
-                            smem_xor(a + 4u, x1 ? bit : 0u);
+                            smem_xor(a, (flip & 1u) ? bit : 0u);
+                            smem_xor(a + 4u, (flip & 2u) ? bit : 0u);
                         }
                 }
+                xm = __funnelshift_r(xm, xm, 2);
             }
-            if (j0 + (t & ~31) < N) {
-                const uint32_t w0 = __ballot_sync(0xffffffffu, x0);
-                const uint32_t w1 = __ballot_sync(0xffffffffu, x1);
-                if (lane == 0) dec[j >> 5] = make_uint2(w0, w1);
-            }
+            xm = __funnelshift_l(xm, xm, 2 * rounds);  // back to round 0 in the low bits
         }
         group_sync(bar, T);
         // ---- candidate syndrome == syndrome ?  (bp.hpp:292-308); every warp reads the words itself ----
@@ -230,22 +254,14 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
         const bool bad1 = __any_sync(0xffffffffu, v1 != 0);
         const bool done0 = idx0 >= 0 && (!bad0 || it0 >= p.max_iter);
         const bool done1 = idx1 >= 0 && (!bad1 || it1 >= p.max_iter);
-        // ---- retire ----
+        // ---- retire: every thread writes the decisions of its own columns ----
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (!(h ? done1 : done0)) continue;
             const long long idx = h ? idx1 : idx0;
-            const uint32_t *d = reinterpret_cast<const uint32_t *>(dec) + h;
             uint8_t *drow = p.out_dec + idx * n;
-            if ((n & 3) == 0) {
-                uint32_t *o32 = reinterpret_cast<uint32_t *>(drow);
-                for (int w = t; w < (n >> 2); w += T) {
-                    const uint32_t bits = d[2 * (w >> 3)] >> ((w & 7) * 4);
-                    o32[w] = (bits & 1u) | ((bits & 2u) << 7) | ((bits & 4u) << 14) | ((bits & 8u) << 21);
-                }
-            } else {
-                for (int j = t; j < n; j += T) drow[j] = (uint8_t) ((d[2 * (j >> 5)] >> (j & 31)) & 1u);
-            }
+            uint32_t bits = xm >> h;
+            for (int j = t; j < n; j += T, bits >>= 2) drow[j] = (uint8_t) (bits & 1u);
             if (t == 0) {
                 if (p.out_iters) p.out_iters[idx] = h ? it1 : it0;
                 if (p.out_conv) p.out_conv[idx] = (h ? bad1 : bad0) ? 0 : 1;

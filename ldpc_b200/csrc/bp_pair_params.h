@@ -9,9 +9,9 @@ struct PairParams {
     uint32_t tab_bytes;   // multiple of 16
     uint32_t off_row_deg, off_col_deg, off_col_row, off_row_pos, off_col_pos, off_prior;  // byte offsets in the blob
     uint32_t group_bytes;                                      // per-group area (multiple of 16)
-    uint32_t goff_msg, goff_dec, goff_syn, goff_acc, goff_ctl;  // byte offsets inside a group area
+    uint32_t goff_msg, goff_syn, goff_acc, goff_ctl;  // byte offsets inside a group area
     int m, n, M, N;       // M, N: padded row / column counts (table strides, multiples of 32)
-    int MW, NW;           // 32-bit words per syndrome ceil(m / 32), per decision vector N / 32
+    int MW;               // 32-bit words per syndrome ceil(m / 32)
     int groups, T;        // thread groups per CTA, threads per group (multiple of 32)
     int max_iter;
     double ms_scaling;

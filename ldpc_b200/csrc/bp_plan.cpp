@@ -351,12 +351,10 @@ void build_pair_plan(bpb_decoder *h) {
     uint32_t go = 0;
     pl.goff_msg = go;
     go += 16u * (uint32_t) pl.msg_slots;
-    pl.goff_dec = go;
-    go += 2u * (uint32_t) N / 8;  // one bit per column, two syndromes
     pl.goff_syn = go;
-    go += 2u * 4u * MW;           // two packed syndromes
+    go += 2u * 4u * MW;  // two packed syndromes, interleaved word by word
     pl.goff_acc = go;
-    go += 2u * 2u * 4u * MW;      // candidate accumulators: two buffers x two syndromes
+    go += 2u * 4u * MW;  // syndrome ^ candidate syndrome of the two halves, interleaved
     go = align_up(go, 8);
     pl.goff_ctl = go;
     go += 16;
