@@ -550,6 +550,7 @@ int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.M = pl.M;
     p.N = pl.N;
     p.MW = (g.m + 31) / 32;
+    p.msg_slots = pl.msg_slots;
     p.groups = G;
     p.T = T;
     p.max_iter = h->max_iter;

@@ -46,7 +46,7 @@ __device__ __forceinline__ double2 lds128(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
-// shared-memory word ^= bit (reduction: no return value)
+// shared-memory word ^= bit (reduction: no return value; 64-bit XOR reductions would be emulated with a CAS loop)
 __device__ __forceinline__ void smem_xor(uint32_t addr, uint32_t bit) {
     asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(addr), "r"(bit) : "memory");
 }
@@ -126,7 +126,14 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
                 for (int w = t; w < MW; w += T) acc[w].y = synw[w].y = __ldg(srow + w);
                 xm &= 0x55555555u;
             }
-            if (f0 || f1) {
+            if ((f0 || f1) && p.uniform_prior) {
+                // every message starts as the same prior: fill the slots linearly, no table lookups
+                double2 *q = reinterpret_cast<double2 *>(garea + p.goff_msg);
+                for (int s = t; s < p.msg_slots; s += T) {
+                    if (f0) q[s].x = p.prior0;
+                    if (f1) q[s].y = p.prior0;
+                }
+            } else if (f0 || f1) {
                 for (int j = t; j < n; j += T) {
                     const int deg = UNI ? DV : col_deg[j];
                     const double pr = p.uniform_prior ? p.prior0 : prior[j];
@@ -182,20 +189,16 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
         const bool llr0_on = LLR && idx0 >= 0 && (!p.llr_last_only || it0 == p.max_iter);
         const bool llr1_on = LLR && idx1 >= 0 && (!p.llr_last_only || it1 == p.max_iter);
         {
-            uint32_t wn[DVp], crn[DVp];
+            uint32_t wn[DVp];
 #pragma unroll
-            for (int q = 0; q < DVp; ++q) {
-                wn[q] = (t < n) ? col_pos[q * N + t] : 0u;
-                crn[q] = (t < n) ? col_row[q * N + t] : 0u;
-            }
+            for (int q = 0; q < DVp; ++q) wn[q] = (t < n) ? col_pos[q * N + t] : 0u;
             int rounds = 0;
             for (int j = t; j < n; j += T, ++rounds) {
                 const int deg = UNI ? DV : col_deg[j];
-                uint32_t pos[DV], cr[DVp];
+                uint32_t pos[DV];
                 double c0[DV], c1[DV];
 #pragma unroll
                 for (int q = 0; q < DVp; ++q) {
-                    cr[q] = crn[q];
                     pos[2 * q] = slot_addr(msg_s, wn[q], 0);
                     if (2 * q + 1 < DV) pos[2 * q + 1] = slot_addr(msg_s, wn[q], 1);
                 }
@@ -208,10 +211,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
                 }
                 if (j + T < n) {
 #pragma unroll
-                    for (int q = 0; q < DVp; ++q) {
-                        wn[q] = col_pos[q * N + j + T];
-                        crn[q] = col_row[q * N + j + T];
-                    }
+                    for (int q = 0; q < DVp; ++q) wn[q] = col_pos[q * N + j + T];
                 }
                 const double pr = p.uniform_prior ? p.prior0 : prior[j];
                 const double llr0 = bit_node_update<DV>(c0, deg, pr);
@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
                 const uint32_t now = ((llr0 <= 0) ? 1u : 0u) | ((llr1 <= 0) ? 2u : 0u);
                 const uint32_t flip = (xm ^ now) & 3u;
                 xm ^= flip;
-                if (flip) {
+                if (flip) {  // few columns flip after the first iterations: the row indices are fetched only here
+                    uint32_t cr[DVp];
+#pragma unroll
+                    for (int q = 0; q < DVp; ++q) cr[q] = (2 * q < deg) ? col_row[q * N + j] : 0u;
 #pragma unroll
                     for (int k = 0; k < DV; ++k)
                         if (k < deg) {

@@ -12,6 +12,7 @@ struct PairParams {
     uint32_t goff_msg, goff_syn, goff_acc, goff_ctl;  // byte offsets inside a group area
     int m, n, M, N;       // M, N: padded row / column counts (table strides, multiples of 32)
     int MW;               // 32-bit words per syndrome ceil(m / 32)
+    int msg_slots;        // double2 slots of one group's message array
     int groups, T;        // thread groups per CTA, threads per group (multiple of 32)
     int max_iter;
     double ms_scaling;
