@@ -79,7 +79,7 @@ def config_table(idx):
                     metric="syndrome decodes/sec (BP+OSD-0) on [[144,12,12]] bivariate bicycle code")
     if idx == 5:
         return dict(idx=5, label="(3,6)-regular LDPC n=10000 (seed 1), min_sum SERIAL max_iter=100 ms_scaling=0.625",
-                    H=lambda: c.regular_ldpc(10000, 3, 6, seed=1), p=0.05, syndromes="bsc", batch=1 << 18, osd=False,
+                    H=lambda: c.regular_ldpc(10000, 3, 6, seed=1), p=0.05, syndromes="bsc", batch=1 << 19, osd=False,
                     sweep=(0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08),
                     kw=dict(max_iter=100, bp_method="ms", schedule="serial", ms_scaling_factor=0.625),
                     metric="syndrome decodes/sec (100 serial BP iters) on n=10000 (3,6)-LDPC")

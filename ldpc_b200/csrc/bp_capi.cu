@@ -1006,12 +1006,11 @@ int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, i
                  h->pair_plan.why;
         return BPB_ERR_UNSUPPORTED;
     }
-    // AUTO: the paired kernels (two syndromes per thread group) for min-sum when they can take the code; product-sum
-    // is arithmetic-bound and keeps the one-syndrome groups
+    // AUTO: the paired kernels (two syndromes per thread group) when they can take the code: config 2 (min-sum)
+    // 28.7 vs 22.4 M decodes/s for one-syndrome groups, config 3 (product-sum, arithmetic-bound) 4.83 vs 4.59
     const bool use_pair = !use_edge && pair_able(h) &&
                           (h->kernel_pref == BPB_KERNEL_PAIR ||
-                           (h->kernel_pref == BPB_KERNEL_AUTO && h->method == BPB_MINIMUM_SUM &&
-                            !std::getenv("BPB_NO_PAIR_AUTO")));
+                           (h->kernel_pref == BPB_KERNEL_AUTO && !std::getenv("BPB_NO_PAIR_AUTO")));
     const bool use_smem = !use_edge && !use_pair && smem_able &&
                           (h->kernel_pref == BPB_KERNEL_SMEM ||
                            (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
@@ -1120,7 +1119,16 @@ int host_pipeline(bpb_decoder *h, int input_type, const uint8_t *input, int64_t 
                                                (h->kernel_pref == BPB_KERNEL_AUTO && h->schedule == BPB_PARALLEL));
     const size_t row_bytes = (size_t) in_w + (size_t) g.n * (bp_decoding ? 2 : 1) + 5 +
                              ((llr || with_osd) ? (size_t) g.n * 8 : 0);
-    const int64_t chunk_max = chunk_rows(smem_able ? ((int64_t) 1 << 17) : ((int64_t) 1 << 20), row_bytes, batch);
+    const size_t io_bytes = (size_t) in_w + (size_t) g.n * (bp_decoding ? 2 : 1) + 5 + (llr ? (size_t) g.n * 8 : 0);
+    // on-chip families: the first chunk's H2D and the last chunk's D2H are not hidden behind a kernel, so keep chunks
+    // small (2^16 rows = 1/16 of the 2^20 workload); each chunk still gives every SM hundreds of syndromes
+    // (2^16 rows of n = 1000, but at least 32 MB of input + output per chunk: small codes pay per-chunk overheads)
+    int64_t want_rows = smem_able ? std::min<int64_t>((int64_t) 1 << 18,
+                                                      std::max<int64_t>((int64_t) 1 << 16,
+                                                                        ((int64_t) 32 << 20) / (int64_t) io_bytes))
+                                  : ((int64_t) 1 << 20);
+    if (const char *ov = std::getenv("BPB_CHUNK_ROWS")) want_rows = std::max<int64_t>(1024, std::atoll(ov));  // tuning
+    const int64_t chunk_max = chunk_rows(want_rows, row_bytes, batch);
     const size_t cap = (size_t) chunk_max;
     // Pageable input (e.g. a plain numpy array): cudaMemcpyAsync would go through the driver's single staging buffer
     // at a few GB/s and block.  Stage it ourselves: a few host threads copy the chunk into a pinned slot buffer while

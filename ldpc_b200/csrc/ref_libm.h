@@ -292,9 +292,6 @@ RL_FN double rl_expm1(double x0) {
     const uint32_t hw = (uint32_t) (bits >> 32);
     const uint32_t hx = hw & 0x7fffffffu;
     const bool neg = (hw & 0x80000000u) != 0;
-    double x = x0, c = 0.0;
-    int k = 0;
-    bool reduce = false;   // general k = round(x/ln2)
     if (hx > 0x40436879u) {          // |x| >= 56 ln2
         if (hx > 0x40862e41u) {      // |x| >= 709.78
             if (hx > 0x7fefffffu) {  // inf / NaN
@@ -304,36 +301,23 @@ RL_FN double rl_expm1(double x0) {
             if (x0 > 0x1.62e42fefa39efp+9) return RL_MUL(1e300, 1e300);  // overflow -> inf
         }
         if (neg) return RL_SUB(1e-300, 1.0);  // x < -56 ln2: -1 (inexact)
-        reduce = true;
-    } else if (hx > 0x3fd62e42u) {   // |x| > 0.5 ln2
-        if (hx > 0x3ff0a2b1u) {
-            reduce = true;           // |x| >= 1.5 ln2
-        } else {
-            double hi, lo;
-            if (!neg) {
-                hi = RL_SUB(x0, ln2_hi);
-                lo = ln2_lo;
-                k = 1;
-            } else {
-                hi = RL_ADD(x0, ln2_hi);
-                lo = -ln2_lo;
-                k = -1;
-            }
-            x = RL_SUB(hi, lo);
-            c = RL_SUB(RL_SUB(hi, x), lo);
-        }
     } else if (hx <= 0x3c8fffffu) {  // |x| < 2^-54
         return x0;
     }
-    if (reduce) {
-        const double kf = RL_ADD(neg ? -0.5 : 0.5, RL_MUL(x0, invln2));
-        k = RL_D2I(kf);
-        const double t = (double) k;
-        const double hi = RL_FMA(-t, ln2_hi, x0);
-        const double lo = RL_MUL(t, ln2_lo);
-        x = RL_SUB(hi, lo);
-        c = RL_SUB(RL_SUB(hi, x), lo);
-    }
+    // Argument reduction x0 = k ln2 + x, without branches (lanes of a warp differ in k).  fdlibm has three cases:
+    // |x| <= 0.5 ln2: k = 0, x = x0, c = 0;  0.5 ln2 < |x| < 1.5 ln2: k = +-1 with hi = x0 -+ ln2_hi, lo = +-ln2_lo;
+    // else k = (int)(x0/ln2 +- 0.5), hi = x0 - k ln2_hi (one rounding: FMA in the __expm1_fma variant), lo = k ln2_lo.
+    // The third formula reproduces the other two operation for operation: for k = +-1 the FMA is the same single
+    // rounding of x0 -+ ln2_hi and k ln2_lo = +-ln2_lo exactly (the hx thresholds sit strictly inside
+    // (0.5, 1.5) ln2, so the truncation gives +-1 there); for k = 0 it gives hi = x0, lo = +0, x = x0, c = +0.
+    const bool small = hx <= 0x3fd62e42u;  // |x| <= 0.5 ln2 (by the high word, as fdlibm tests it)
+    const double kf = RL_ADD(neg ? -0.5 : 0.5, RL_MUL(x0, invln2));
+    const int k = small ? 0 : RL_D2I(kf);
+    const double tk = (double) k;
+    const double rhi = RL_FMA(-tk, ln2_hi, x0);
+    const double rlo = RL_MUL(tk, ln2_lo);
+    const double x = RL_SUB(rhi, rlo);
+    const double c = RL_SUB(RL_SUB(rhi, x), rlo);
     // x is now in the primary range
     const double hfx = RL_MUL(x, 0.5);
     const double hxs = RL_MUL(x, hfx);
@@ -388,13 +372,12 @@ RL_FN double rl_tanh(double x) {
         if ((ix | (uint32_t) bits) == 0) return x;                         // +-0
         if (ix < 0x3c800000u) return RL_MUL(x, RL_ADD(1.0, x));           // |x| < 2^-55
         const double ax = RL_DBL(bits & 0x7fffffffffffffffull);
-        if (ix >= 0x3ff00000u) {                                           // |x| >= 1
-            const double t = rl_expm1(RL_MUL(2.0, ax));
-            z = RL_SUB(1.0, RL_DIV(2.0, RL_ADD(t, 2.0)));
-        } else {
-            const double t = rl_expm1(RL_MUL(-2.0, ax));
-            z = RL_DIV(-t, RL_ADD(t, 2.0));
-        }
+        // |x| >= 1: t = expm1(2|x|), z = 1 - 2/(t+2);  |x| < 1: t = expm1(-2|x|), z = -t/(t+2).  One expm1 and one
+        // division serve both cases (the lanes of a warp straddle |x| = 1 all the time).
+        const bool big = ix >= 0x3ff00000u;
+        const double t = rl_expm1(RL_MUL(big ? 2.0 : -2.0, ax));
+        const double q = RL_DIV(big ? 2.0 : -t, RL_ADD(t, 2.0));
+        z = big ? RL_SUB(1.0, q) : q;
     } else {
         z = 1.0;              // 1 - tiny rounds to 1
     }
