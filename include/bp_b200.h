@@ -34,8 +34,9 @@ enum { BPB_OK = 0, BPB_ERR_ARG = -1, BPB_ERR_CUDA = -2, BPB_ERR_UNSUPPORTED = -3
 
 /* ldpc::bp::BpMethod, bp.hpp:23-26 */
 enum { BPB_PRODUCT_SUM = 0, BPB_MINIMUM_SUM = 1 };
-/* ldpc::bp::BpSchedule, bp.hpp:28-32 (SERIAL_RELATIVE = 2 is not offered on the GPU) */
-enum { BPB_SERIAL = 0, BPB_PARALLEL = 1 };
+/* ldpc::bp::BpSchedule, bp.hpp:28-32.  SERIAL_RELATIVE re-sorts the schedule by posterior LLR before every sweep
+ * (bp.hpp:469-482); every syndrome of a batch starts from the configured serial_schedule_order. */
+enum { BPB_SERIAL = 0, BPB_PARALLEL = 1, BPB_SERIAL_RELATIVE = 2 };
 /* ldpc::bp::BpInputType, bp.hpp:34-38 */
 enum { BPB_INPUT_SYNDROME = 0, BPB_INPUT_RECEIVED_VECTOR = 1 };
 /* kernel family: AUTO picks the fastest family that supports the code (STREAM: a lane per syndrome, messages in HBM;
@@ -65,6 +66,9 @@ int bpb_set_method(bpb_decoder *h, int bp_method);                              
 int bpb_set_schedule(bpb_decoder *h, int schedule);                              /* bp.hpp:60 */
 int bpb_set_ms_scaling_factor(bpb_decoder *h, double ms_scaling_factor);         /* bp.hpp:62 */
 int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len); /* bp.hpp:69; NULL = 0..n-1 */
+/* SERIAL_RELATIVE: the schedule the LAST syndrome of the most recent decode call ended with -- what the reference's
+ * serial_schedule_order member holds after that decode (bp.hpp:469-482 sorts it in place).  Synchronises. */
+int bpb_get_last_schedule_order(bpb_decoder *h, int32_t *out, int len);
 int bpb_set_kernel(bpb_decoder *h, int kernel_family);                           /* new: BPB_KERNEL_* */
 int bpb_set_osd_location(bpb_decoder *h, int osd_location);                      /* new: BPB_OSD_* */
 /* new: split every HOST-pointer batch call of this handle over `count` CUDA devices.  One

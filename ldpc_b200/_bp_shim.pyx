@@ -59,6 +59,8 @@ cdef extern from "bp_b200.h":
     int bpb_get_info(const bpb_decoder *h, bpb_info *out) nogil
     int bpb_set_osd_location(bpb_decoder *h, int v) nogil
     int bpb_set_devices(bpb_decoder *h, const int *ids, int count) nogil
+    int bpb_get_last_schedule_order(bpb_decoder *h, int32_t *out, int len) nogil
+    int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len) nogil
     int bpb_mc_bsc(bpb_decoder *h, uint64_t seed, int64_t first_run, int64_t runs, const double *flip_prob,
                    int with_osd, int64_t *counts) nogil
 
@@ -132,6 +134,20 @@ cdef class NativeHandle:
 
     def set_osd_location(self, int v):
         self._check(bpb_set_osd_location(self.h, v))
+
+    def last_schedule_order(self, int32_t[::1] out):
+        cdef int rc
+        cdef int k = <int> out.shape[0]
+        with nogil:
+            rc = bpb_get_last_schedule_order(self.h, &out[0], k)
+        self._check(rc)
+
+    def set_order(self, const int32_t[::1] order):
+        cdef int rc
+        cdef int k = <int> order.shape[0]
+        with nogil:
+            rc = bpb_set_serial_schedule_order(self.h, &order[0], k)
+        self._check(rc)
 
     def set_devices(self, const int32_t[::1] ids):
         cdef int k = <int> ids.shape[0]

@@ -44,7 +44,7 @@ EXPORTS = [
     "bpb_set_schedule", "bpb_set_ms_scaling_factor", "bpb_set_serial_schedule_order", "bpb_set_kernel",
     "bpb_decode_batch", "bpb_decode_batch_device", "bpb_osd0_host", "bpb_bposd_decode_batch", "bpb_get_info", "bpb_host_alloc",
     "bpb_host_free", "bpb_version", "bpb_set_osd_location", "bpb_set_devices", "bpb_bposd_decode_batch_device",
-    "bpb_mc_bsc",
+    "bpb_mc_bsc", "bpb_get_last_schedule_order",
 ]
 
 _lib = None
@@ -97,6 +97,8 @@ def lib():
     L.bpb_set_devices.argtypes = [vp, _i32p, C.c_int]
     L.bpb_bposd_decode_batch_device.restype = C.c_int
     L.bpb_bposd_decode_batch_device.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp]
+    L.bpb_get_last_schedule_order.restype = C.c_int
+    L.bpb_get_last_schedule_order.argtypes = [vp, _i32p, C.c_int]
     L.bpb_mc_bsc.restype = C.c_int
     L.bpb_mc_bsc.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, _f64p, C.c_int, C.POINTER(C.c_int64)]
     _lib = L
@@ -154,7 +156,8 @@ def pinned_empty(shape, dtype):
     dtype = np.dtype(dtype)
     count = int(np.prod(shape))
     need = max(4096, count * dtype.itemsize)
-    nbytes = 1 << (need - 1).bit_length()
+    # buckets: powers of two up to 64 MiB, multiples of 64 MiB above (a power of two would pin up to 2x the request)
+    nbytes = 1 << (need - 1).bit_length() if need <= (64 << 20) else -(-need // (64 << 20)) * (64 << 20)
     ptr = None
     with _POOL_LOCK:
         free = _POOL.get(nbytes)

@@ -99,6 +99,21 @@ class Handle:
             return self._wrap(self._nh.set_osd_location, int(where))
         _capi.check(self._ct, _capi.lib().bpb_set_osd_location(self._ct, int(where)))
 
+    def last_schedule_order(self, n):
+        """SERIAL_RELATIVE: the schedule the last syndrome of the last decode call ended with."""
+        out = np.empty(n, dtype=np.int32)
+        if self._nh is not None:
+            self._wrap(self._nh.last_schedule_order, out)
+            return out
+        _capi.check(self._ct, _capi.lib().bpb_get_last_schedule_order(self._ct, out.ctypes.data_as(_capi._i32p), n))
+        return out
+
+    def set_order(self, order):
+        od = np.ascontiguousarray(order, dtype=np.int32)
+        if self._nh is not None:
+            return self._wrap(self._nh.set_order, od)
+        _capi.check(self._ct, _capi.lib().bpb_set_serial_schedule_order(self._ct, od.ctypes.data_as(_capi._i32p), od.size))
+
     def set_devices(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         if self._nh is not None:

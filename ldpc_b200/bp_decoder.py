@@ -7,9 +7,10 @@ exception types, properties, the all-zero shortcut and the output-dtype echo of 
 (``_bp_decoder.pyx:642-695``).  New on top: ``decode_batch`` and the ``device=`` keyword.
 
 All decoding happens in hand-written sm_100a CUDA behind ``include/bp_b200.h``; there is no CPU
-fallback.  Options the GPU path does not implement (``serial_relative`` schedule, random serial schedule;
-DESIGN.md "out of scope") raise ``NotImplementedError`` at decode time rather than silently changing
-behaviour.
+fallback.  ``schedule='serial_relative'`` (the schedule re-sorted by posterior LLR before every sweep, with
+libstdc++'s ``std::sort`` restated on the device) is supported; the random serial schedule (a shared RNG stream
+that advances per iteration, DESIGN.md "out of scope") raises ``NotImplementedError`` at decode time rather
+than silently changing behaviour.
 """
 from __future__ import annotations
 
@@ -119,8 +120,6 @@ class BpDecoderBase:
                 # contiguous slices, the D2H copies land in disjoint ranges of the output arrays
                 self._native.set_devices(self._devices)
         if self._dirty:
-            if self._schedule == _capi.SERIAL_RELATIVE:
-                raise NotImplementedError("schedule='serial_relative' is not implemented on the GPU path")
             if self._random_serial_schedule:
                 raise NotImplementedError("random_serial_schedule is not implemented on the GPU path")
             kern = {"auto": _capi.KERNEL_AUTO, "stream": _capi.KERNEL_STREAM, "smem": _capi.KERNEL_SMEM,
@@ -131,13 +130,19 @@ class BpDecoderBase:
             self._dirty = False
         return self._handle
 
-    def _decode_device_batch(self, inputs: np.ndarray, input_type: int, want_llr: bool):
+    def _decode_device_batch(self, inputs: np.ndarray, input_type: int, want_llr: bool, out=None):
         """inputs: contiguous uint8 [B, m|n].  Returns (decoding u8 [B,n], converged bool[B], iters i32[B], llr|None)."""
         self._ensure_handle()
         B = inputs.shape[0]
         big = B * self.n >= (1 << 20)  # large results land in pinned memory (asynchronous D2H at full PCIe speed)
         alloc = _capi.pinned_empty if big else np.empty
-        dec = alloc((B, self.n), dtype=np.uint8)
+        if out is not None:
+            if not (isinstance(out, np.ndarray) and out.dtype == np.uint8 and out.shape == (B, self.n)
+                    and out.flags.c_contiguous and out.flags.writeable):
+                raise ValueError(f"out must be a writable C-contiguous uint8 array of shape ({B}, {self.n})")
+            dec = out
+        else:
+            dec = alloc((B, self.n), dtype=np.uint8)
         conv = alloc((B,), dtype=np.uint8)
         its = alloc((B,), dtype=np.int32)
         llr = alloc((B, self.n), dtype=np.float64) if want_llr else None
@@ -402,14 +407,24 @@ class BpDecoder(BpDecoderBase):
             self._converge = True
             return np.zeros(self.n, dtype=dtype)
         dec, conv, its, llr = self._decode_device_batch(vec, kind, want_llr=True)
+        if self._schedule == _capi.SERIAL_RELATIVE and self._devices is None:
+            # the reference sorts its serial_schedule_order member in place in every iteration (bp.hpp:469-482) and
+            # the object carries it into its next decode: mirror that state (decode_batch does not: every row of a
+            # batch starts from the configured order)
+            order = self._native.last_schedule_order(len(self._serial_schedule_order))
+            self._serial_schedule_order = order.astype(np.int64)
+            self._native.set_order(order)
         self._decoding = dec[0]
         self._converge = bool(conv[0])
         self._iterations = int(its[0])
         self._log_prob_ratios = llr[0]
         return dec[0].astype(dtype)
 
-    def decode_batch(self, input_vectors: np.ndarray, return_llr: bool = False) -> np.ndarray:
+    def decode_batch(self, input_vectors: np.ndarray, return_llr: bool = False, out=None) -> np.ndarray:
         """Decode ``[B, m]`` syndromes (or ``[B, n]`` received vectors) in one GPU call.
+
+        ``out``: optional preallocated uint8 ``[B, n]`` result array (numpy style; pinned memory from
+        ``ldpc_b200._capi.PinnedArray`` makes the device-to-host copies asynchronous).
 
         Every row is decoded exactly as ``BpDecoder::decode`` would decode it on its own (reference
         src_cpp/bp.hpp:159-190), i.e. with the C++ semantics: an all-zero syndrome runs one iteration and
@@ -427,7 +442,7 @@ class BpDecoder(BpDecoderBase):
             self.iter_batch = np.zeros(0, np.int32)
             self.log_prob_ratios_batch = np.zeros((0, self.n)) if return_llr else None
             return np.zeros((0, self.n), dtype=dtype)
-        dec, conv, its, llr = self._decode_device_batch(vec, kind, want_llr=return_llr)
+        dec, conv, its, llr = self._decode_device_batch(vec, kind, want_llr=return_llr, out=out)
         self.converge_batch, self.iter_batch, self.log_prob_ratios_batch = conv, its, llr
         return dec if dtype == np.uint8 else dec.astype(dtype)
 

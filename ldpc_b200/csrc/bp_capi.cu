@@ -54,7 +54,7 @@ std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
             &h->packed,   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
             &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1],
             &h->st_bp[0],   &h->st_bp[1],   &h->osd_conv,  &h->mc_thresh, &h->mc_err, &h->mc_syn, &h->mc_dec,
-            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg, &h->pair_tab};
+            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg, &h->pair_tab, &h->rel_order, &h->rel_order_out, &h->rel_msg};
 }
 
 void release(bpb::DeviceBuffer &b) {
@@ -191,6 +191,15 @@ int upload_graph(bpb_decoder *h) {
         h->serial_order.resize((size_t) g.n);
         for (int j = 0; j < g.n; j++) h->serial_order[(size_t) j] = (uint32_t) j;
     }
+    // SERIAL_RELATIVE: the configured order as it is (the kernel sorts its own copy per syndrome)
+    rc = ensure(h, h->rel_order, h->serial_order.size() * sizeof(uint32_t));
+    if (rc) return rc;
+    BPB_CUDA(h, cudaMemcpy(h->rel_order.ptr, h->serial_order.data(), h->serial_order.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice));
+    rc = ensure(h, h->rel_order_out, h->serial_order.size() * sizeof(int32_t));
+    if (rc) return rc;
+    h->rel_order_valid = false;
+    h->order_dirty = false;
     const int sb = bpb::serial_batch(g.max_row_degree, g.max_col_degree, g.regular);
     h->serial_batches = build_serial_batches(g, h->serial_order, sb);
     std::vector<uint32_t> upload = h->serial_batches;
@@ -856,9 +865,9 @@ int bpb_set_method(bpb_decoder *h, int v) {
 
 int bpb_set_schedule(bpb_decoder *h, int v) {
     if (!h) return BPB_ERR_ARG;
-    if (v != BPB_SERIAL && v != BPB_PARALLEL) {
+    if (v != BPB_SERIAL && v != BPB_PARALLEL && v != BPB_SERIAL_RELATIVE) {
         h->err = "Invalid BP schedule";  // bp.hpp:171
-        return v == 2 ? BPB_ERR_UNSUPPORTED : BPB_ERR_ARG;
+        return BPB_ERR_ARG;
     }
     if (h->schedule != v) h->graph_dirty = true;  // the shared-memory plan depends on the schedule
     h->schedule = v;
@@ -900,7 +909,11 @@ int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len)
             return BPB_ERR_ARG;
         }
     h->serial_order.assign(order, order + len);
-    h->graph_dirty = true;
+    // SERIAL_RELATIVE only reads the raw schedule (no levelisation, no tables depend on it): re-upload just that
+    if (h->schedule == BPB_SERIAL_RELATIVE && !h->graph_dirty && h->rel_order.bytes >= (size_t) len * 4)
+        h->order_dirty = true;
+    else
+        h->graph_dirty = true;
     for (bpb_decoder *c: h->children) {
         const int rc_c = bpb_set_serial_schedule_order(c, order, len);
         if (rc_c) {
@@ -908,6 +921,22 @@ int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len)
             return rc_c;
         }
     }
+    return BPB_OK;
+}
+
+int bpb_get_last_schedule_order(bpb_decoder *h, int32_t *out, int len) {
+    if (!h || !out) return BPB_ERR_ARG;
+    if (h->device < 0 || !h->rel_order_valid || h->schedule != BPB_SERIAL_RELATIVE) {
+        h->err = "no SERIAL_RELATIVE decode has run on this handle since the last configuration change";
+        return BPB_ERR_ARG;
+    }
+    if (len != (int) h->serial_order.size()) {
+        h->err = "schedule length mismatch";
+        return BPB_ERR_ARG;
+    }
+    BPB_CUDA(h, cudaSetDevice(h->device));
+    BPB_CUDA(h, cudaDeviceSynchronize());
+    BPB_CUDA(h, cudaMemcpy(out, h->rel_order_out.ptr, sizeof(int32_t) * (size_t) len, cudaMemcpyDeviceToHost));
     return BPB_OK;
 }
 
@@ -981,6 +1010,51 @@ int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, i
     }
     BPB_CUDA(h, cudaGetLastError());
     if (input_type != kInputPacked) h->launches += 1;
+    if (h->schedule == BPB_SERIAL_RELATIVE) {
+        // data-dependent schedule: its own kernel (one warp per syndrome, bp_relative.cu), whatever the family preference
+        if (h->order_dirty) {
+            BPB_CUDA(h, cudaStreamSynchronize(st));  // earlier decodes may still read the schedule
+            BPB_CUDA(h, cudaMemcpy(h->rel_order.ptr, h->serial_order.data(), h->serial_order.size() * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice));
+            h->order_dirty = false;
+        }
+        if ((rc = ensure(h, h->counter, 64))) return rc;
+        BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+        int grid = 0;
+        BPB_CUDA(h, cudaEventRecord(h->kev0, st));
+        const int e = bpb::launch_relative_kernel(g, h->sm_count, h->max_smem_optin, (const uint32_t *) h->blob.ptr,
+                                                  h->prior_off, h->method, h->max_iter, h->ms_scaling,
+                                                  (const uint32_t *) h->rel_order.ptr, (int) h->serial_order.size(),
+                                                  d_packed, mwp, batch, (unsigned long long *) h->counter.ptr + 2,
+                                                  &h->rel_msg, d_decoding, d_converged, d_iterations, d_llr,
+                                                  h->llr_last_only ? 1 : 0, (int32_t *) h->rel_order_out.ptr, st, &grid);
+        if (e == -1) {
+            h->err = "SERIAL_RELATIVE: the code does not fit the kernel (column degree > 32 or n beyond shared memory)";
+            return BPB_ERR_UNSUPPORTED;
+        }
+        if (e) {
+            h->err = std::string("bp_relative_kernel launch: ") + cudaGetErrorString((cudaError_t) e);
+            return BPB_ERR_CUDA;
+        }
+        BPB_CUDA(h, cudaEventRecord(h->kev1, st));
+        h->kernel_timed = true;
+        h->rel_order_valid = true;
+        h->launches += 1;
+        h->last_family = BPB_KERNEL_EDGE;  // a cooperative (warp per syndrome) kernel
+        h->last_grid = grid;
+        h->last_block = 32;
+        if (input_type == BPB_INPUT_RECEIVED_VECTOR) {
+            const long long count = (long long) batch * g.n;
+            const int xgrid = (int) std::min<long long>((count + 255) / 256, (long long) h->sm_count * 32);
+            xor_received_kernel<<<xgrid, 256, 0, st>>>(d_decoding, d_input, count);
+            BPB_CUDA(h, cudaGetLastError());
+            h->launches += 1;
+        }
+        BPB_CUDA(h, cudaEventRecord(h->ev_last, st));
+        h->last_stream = st;
+        h->have_last = true;
+        return BPB_OK;
+    }
     // family: the on-chip kernels serve the parallel schedule of codes whose messages fit in shared memory;
     // everything else (serial schedule, large codes) streams its messages through HBM.
     const bool smem_able = h->smem_plan.ok;

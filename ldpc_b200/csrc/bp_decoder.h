@@ -71,6 +71,14 @@ int launch_osd0_kernel(const OsdDevicePlan &pl, const HostGraph &g, int sm_count
                        const uint32_t *d_fail_idx, const unsigned long long *d_count, unsigned long long *d_counter,
                        uint8_t *d_dec, int64_t max_items, cudaStream_t st);
 
+// SERIAL_RELATIVE schedule (bp_relative.cu): one warp per syndrome; returns a cudaError_t value, -1 = does not fit
+int launch_relative_kernel(const HostGraph &g, int sm_count, int max_smem_optin, const uint32_t *d_blob,
+                           uint32_t prior_off, int method, int max_iter, double ms_scaling, const uint32_t *d_order0,
+                           int order_len, const uint32_t *d_packed, int mwp, int64_t batch,
+                           unsigned long long *d_counter, DeviceBuffer *scratch, uint8_t *d_dec, uint8_t *d_conv,
+                           int32_t *d_iters, double *d_llr, int llr_last_only, int32_t *d_order_out, cudaStream_t st,
+                           int *grid_out);
+
 // On-device BSC sampling and scoring (mc_device.cu)
 int launch_mc_generate(const uint32_t *d_row_ptr, const uint32_t *d_col_idx, const unsigned long long *d_thresh, int m,
                        int n, int nw, int mwp, unsigned long long seed, unsigned long long first_run, int64_t batch,
@@ -113,6 +121,9 @@ struct bpb_decoder {
     bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed, smem_tab, handoff;
     bpb::DeviceBuffer osd_llr, osd_fail_llr, osd_fail_idx, osd_count;  // BP+OSD batch path
     bpb::OsdDevicePlan osd_plan;
+    bpb::DeviceBuffer rel_order, rel_order_out, rel_msg;  // SERIAL_RELATIVE: configured / final schedule, scratch
+    bool rel_order_valid = false;  // rel_order_out holds the schedule of a finished decode
+    bool order_dirty = false;      // SERIAL_RELATIVE: only the configured schedule changed (cheap re-upload)
     bpb::DeviceBuffer edge_msg;  // edge-parallel family: message scratch of the resident CTAs (large codes)
     bpb::DeviceBuffer mc_thresh, mc_err, mc_syn, mc_dec, mc_conv, mc_its, mc_counts;  // bpb_mc_bsc workspaces
     int osd_location = BPB_OSD_AUTO;  // where OSD-0 runs in the BP+OSD entry points

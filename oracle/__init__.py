@@ -48,7 +48,7 @@ def _ptr(a, t):
 
 
 _METHODS = {"ps": 0, "product_sum": 0, 0: 0, "ms": 1, "minimum_sum": 1, 1: 1}
-_SCHEDULES = {"serial": 0, "s": 0, "parallel": 1, "p": 1}
+_SCHEDULES = {"serial": 0, "s": 0, "parallel": 1, "p": 1, "serial_relative": 2, "sr": 2}
 
 
 class _Lib:

@@ -40,6 +40,7 @@
 #define BPO_MINIMUM_SUM 1
 #define BPO_SERIAL 0 /* bp.hpp:28-32 */
 #define BPO_PARALLEL 1
+#define BPO_SERIAL_RELATIVE 2
 
 typedef struct {
     int m, n, nnz;
@@ -127,6 +128,7 @@ typedef struct {
     double ms_scaling_factor;
     const int32_t *serial_order; /* n entries */
     int serial_order_len;
+    int *order_work; /* SERIAL_RELATIVE: the evolving serial_schedule_order member */
     /* work */
     double *b2c, *c2b; /* nnz each, CSR edge numbering */
     double *prior;     /* n */
@@ -226,15 +228,142 @@ static void bpo_parallel(bpo_state *s, const uint8_t *syndrome) {
     }
 }
 
-/* bp.hpp:451-545 (SERIAL only; random / relative orders are out of scope) */
+/*
+ * std::sort(order.begin(), order.end(), comp) with comp(a, b) = key[a] > key[b]  (bp.hpp:469-482), as libstdc++
+ * (GCC 13, bits/stl_algo.h, bits/stl_heap.h -- a third-party dependency absent from /root/reference) implements it:
+ * introsort (median of three to the front, unguarded Hoare partition, recursion on the right part, heapsort after
+ * 2*floor(log2 n) levels) followed by the final insertion sort with threshold 16.  The permutation of tied keys is a
+ * property of this algorithm, so it is restated here function by function (recursive, like the original).
+ */
+static const double *bso_key;
+static int bso_comp(int a, int b) { return bso_key[a] > bso_key[b]; }
+static void bso_swap(int *x, int *y) { int t = *x; *x = *y; *y = t; }
+static void bso_move_median_to_first(int *result, int *a, int *b, int *c) {
+    if (bso_comp(*a, *b)) {
+        if (bso_comp(*b, *c)) bso_swap(result, b);
+        else if (bso_comp(*a, *c)) bso_swap(result, c);
+        else bso_swap(result, a);
+    } else if (bso_comp(*a, *c)) bso_swap(result, a);
+    else if (bso_comp(*b, *c)) bso_swap(result, c);
+    else bso_swap(result, b);
+}
+static int *bso_unguarded_partition(int *first, int *last, int *pivot) {
+    for (;;) {
+        while (bso_comp(*first, *pivot)) ++first;
+        --last;
+        while (bso_comp(*pivot, *last)) --last;
+        if (!(first < last)) return first;
+        bso_swap(first, last);
+        ++first;
+    }
+}
+static void bso_push_heap(int *first, long hole, long top, int value) {
+    long parent = (hole - 1) / 2;
+    while (hole > top && bso_comp(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+static void bso_adjust_heap(int *first, long hole, long len, int value) {
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (bso_comp(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    bso_push_heap(first, hole, top, value);
+}
+static void bso_heap_sort(int *first, int *last) {
+    long len = last - first;
+    if (len >= 2) {
+        long parent = (len - 2) / 2;
+        for (;;) {
+            bso_adjust_heap(first, parent, len, first[parent]);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    while (last - first > 1) {
+        --last;
+        int value = *last;
+        *last = *first;
+        bso_adjust_heap(first, 0, last - first, value);
+    }
+}
+static void bso_introsort_loop(int *first, int *last, long depth_limit) {
+    while (last - first > 16) {
+        if (depth_limit == 0) {
+            bso_heap_sort(first, last);
+            return;
+        }
+        --depth_limit;
+        int *mid = first + (last - first) / 2;
+        bso_move_median_to_first(first, first + 1, mid, last - 1);
+        int *cut = bso_unguarded_partition(first + 1, last, first);
+        bso_introsort_loop(cut, last, depth_limit);
+        last = cut;
+    }
+}
+static void bso_unguarded_linear_insert(int *last) {
+    int val = *last;
+    int *next = last - 1;
+    while (bso_comp(val, *next)) {
+        *last = *next;
+        last = next;
+        --next;
+    }
+    *last = val;
+}
+static void bso_insertion_sort(int *first, int *last) {
+    if (first == last) return;
+    for (int *i = first + 1; i != last; ++i) {
+        if (bso_comp(*i, *first)) {
+            int val = *i;
+            memmove(first + 1, first, sizeof(int) * (size_t) (i - first));
+            *first = val;
+        } else {
+            bso_unguarded_linear_insert(i);
+        }
+    }
+}
+static void bso_sort_desc(int *order, int n, const double *key) {
+    if (n <= 0) return;
+    bso_key = key;
+    long lg = 0;
+    while (((long) n >> (lg + 1)) != 0) lg++;
+    bso_introsort_loop(order, order + n, 2 * lg);
+    if (n > 16) {
+        bso_insertion_sort(order, order + 16);
+        for (int *i = order + 16; i != order + n; ++i) bso_unguarded_linear_insert(i);
+    } else {
+        bso_insertion_sort(order, order + n);
+    }
+}
+
+/* bp.hpp:451-545: SERIAL, and SERIAL_RELATIVE (schedule 2, :469-482: the order is re-sorted by descending LLR -- by
+ * the priors in the first iteration -- before every sweep; `order_work` is the decoder's serial_schedule_order member,
+ * which the sort permutes in place).  The random serial schedule is out of scope. */
 static void bpo_serial(bpo_state *s, const uint8_t *syndrome) {
     const bpo_graph *g = s->g;
     s->converge = 0;
     bpo_init(s);
     for (int it = 1; it <= s->max_iter; it++) {
         double alpha = bpo_alpha(s->ms_scaling_factor, it);
+        if (s->schedule == BPO_SERIAL_RELATIVE) {
+            /* bp.hpp:469-482; `prior` holds log((1-p)/p), the key of the first iteration */
+            bso_sort_desc(s->order_work, s->serial_order_len, it != 1 ? s->llr : s->prior);
+        }
         for (int oi = 0; oi < s->serial_order_len; oi++) {
-            int j = s->serial_order[oi];
+            int j = s->schedule == BPO_SERIAL_RELATIVE ? s->order_work[oi] : s->serial_order[oi];
             s->llr[j] = log((1 - s->channel[j]) / s->channel[j]);
             if (s->method == BPO_PRODUCT_SUM) {
                 /* bp.hpp:488-501 */
@@ -337,9 +466,13 @@ int bpo_decode_batch(int m, int n, int64_t nnz, const int32_t *rows, const int32
     s.llr = (double *) calloc((size_t) n + 1, sizeof(double));
     s.decoding = (uint8_t *) calloc((size_t) n + 1, 1);
     s.cand = (uint8_t *) calloc((size_t) m + 1, 1);
+    s.order_work = (int *) calloc((size_t) s.serial_order_len + 1, sizeof(int));
     for (int64_t b = 0; b < batch; b++) {
         const uint8_t *syn = syndromes + b * (int64_t) m;
         s.iterations = 0;
+        /* SERIAL_RELATIVE: every syndrome is decoded as by a freshly constructed decoder, i.e. starting from the
+         * configured order (the reference object would carry the previous decode's final order over) */
+        for (int k = 0; k < s.serial_order_len; k++) s.order_work[k] = s.serial_order[k];
         if (schedule == BPO_PARALLEL)
             bpo_parallel(&s, syn);
         else
@@ -355,6 +488,7 @@ int bpo_decode_batch(int m, int n, int64_t nnz, const int32_t *rows, const int32
     free(s.llr);
     free(s.decoding);
     free(s.cand);
+    free(s.order_work);
     free(ident);
     bpo_graph_free(&g);
     return 0;

@@ -79,9 +79,15 @@ double ref_decode_batch(int m, int n, int64_t nnz, const int32_t *rows, const in
         Worker &w = workers[(size_t) t];
         int64_t lo = batch * t / threads, hi = batch * (t + 1) / threads;
         std::vector<uint8_t> syn((size_t) m);
+        // SERIAL_RELATIVE (bp.hpp:469-482) re-sorts the public member serial_schedule_order in place and the object
+        // carries the result into its next decode; the batch semantics pinned here are "every syndrome as by a freshly
+        // constructed decoder", so the member is put back before each call (a write to a public member, like the
+        // reference's own Python shim does, _bp_decoder.pyx:471-475)
+        const std::vector<int> initial_order = w.bpd->serial_schedule_order;
         auto t0 = std::chrono::steady_clock::now();
         for (int64_t b = lo; b < hi; b++) {
             std::memcpy(syn.data(), syndromes + b * (int64_t) m, (size_t) m);
+            if (schedule == 2) w.bpd->serial_schedule_order = initial_order;
             w.bpd->decode(syn);
             const std::vector<uint8_t> *out = &w.bpd->decoding;
             if (out_bp_decoding) std::memcpy(out_bp_decoding + b * (int64_t) n, w.bpd->decoding.data(), (size_t) n);

@@ -29,12 +29,19 @@ CONFIGS = [
     # configs[4]: serial-schedule min-sum (n=1000 here to keep the fixture small; n=10^4 is run live on the GPU box)
     ("cfg5_ldpc1000_ms_serial", codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 32, 8, dict(max_iter=100, bp_method="ms", schedule="serial", ms_scaling_factor=0.625)),
     ("cfg5_ldpc1000_ps_serial", codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 16, 4, dict(max_iter=50, bp_method="ps", schedule="serial", ms_scaling_factor=1.0)),
+    # SERIAL_RELATIVE (the schedule re-sorted by LLR every iteration, bp.hpp:469-482); every syndrome is
+    # decoded from the initial order 0..n-1 (oracle/ref_wrap.cpp resets the member before each decode)
+    ("f4_ldpc1000_ms_serial_relative", codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 24, 8, dict(max_iter=50, bp_method="ms", schedule="serial_relative", ms_scaling_factor=0.625)),
+    ("f4_bb144_ps_serial_relative", codes.bivariate_bicycle_144(), 0.02, 64, 0, dict(max_iter=30, bp_method="ps", schedule="serial_relative", ms_scaling_factor=1.0)),
 ]
 
 
 def main():
     ref = oracle.RefOracle()
+    only = set(sys.argv[1:])  # optional: names of the fixtures to (re)generate
     for name, H, p, B, Bhard, kw in CONFIGS:
+        if only and name not in only:
+            continue
         syn = codes.bsc_syndromes(H, p, B, seed=7)
         if Bhard:
             syn = np.concatenate([syn, codes.bsc_syndromes(H, 1.8 * p, Bhard, seed=8)])

@@ -7,7 +7,7 @@ import pytest
 
 from ldpc_b200 import BpDecoder, BpOsdDecoder, MonteCarloBscSimulation, _capi, codes
 from ldpc_b200.parallel import MultiGpuBpDecoder
-from util import philox_bsc_errors
+from util import assert_same_decode, philox_bsc_errors
 
 pytestmark = pytest.mark.gpu
 
@@ -203,3 +203,45 @@ def test_pageable_and_pinned_inputs_agree_and_pool_recycles():
     for nb in (1000, 3000, 70000, B // 2, 5, B):
         d.decode_batch(syn[:nb])
     assert _capi._POOL_BYTES[0] <= max(before, 1) * 2 + (64 << 20)  # power-of-two buckets are reused, not leaked
+
+
+@pytest.mark.parametrize("method", ["ms", "ps"])
+def test_serial_relative_schedule_matches_oracle(port_oracle, method):
+    """schedule='serial_relative' (bp.hpp:469-482: the schedule is re-sorted by posterior LLR before
+    every sweep, with libstdc++'s std::sort -- ties and all).  Every row of a batch starts from the configured order.
+    Bar: decisions, converge, iterations exact; LLRs bit-identical for min-sum, 1e-5 for product-sum."""
+    for H, p, B, iters in ((codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 96, 40),
+                           (codes.regular_ldpc(240, 3, 6, seed=3), 0.075, 160, 25),
+                           (codes.rotated_surface_code_x(13), 0.05, 200, 20),
+                           (codes.hamming_code(5), 0.1, 64, 5)):
+        syn = codes.bsc_syndromes(H, p, B, seed=17)
+        kw = dict(max_iter=iters, bp_method=method, schedule="serial_relative", ms_scaling_factor=0.625)
+        want = port_oracle.decode_batch(H, syn, p, **kw)
+        d = BpDecoder(H, error_rate=p, input_vector_type="syndrome", **kw)
+        got = d.decode_batch(syn, return_llr=True)
+        assert_same_decode((got, d.converge_batch, d.iter_batch, d.log_prob_ratios_batch), want,
+                           llr_exact=(method == "ms"))
+
+
+def test_serial_relative_custom_order_and_decode_state(port_oracle):
+    """A custom initial order, and the state the reference object carries from one decode() to the next: its
+    serial_schedule_order member is sorted in place, so decode k+1 starts from the order decode k ended with."""
+    H = codes.regular_ldpc(240, 3, 6, seed=3)
+    order = np.random.default_rng(8).permutation(240)
+    syn = codes.bsc_syndromes(H, 0.07, 40, seed=23)
+    kw = dict(max_iter=25, bp_method="ms", schedule="serial_relative", ms_scaling_factor=0.625)
+    want = port_oracle.decode_batch(H, syn, 0.07, serial_schedule_order=order, **kw)
+    d = BpDecoder(H, error_rate=0.07, input_vector_type="syndrome", serial_schedule_order=[int(x) for x in order], **kw)
+    got = d.decode_batch(syn, return_llr=True)
+    assert_same_decode((got, d.converge_batch, d.iter_batch, d.log_prob_ratios_batch), want, llr_exact=True)
+    # sequential decode(): feed the oracle the order the previous decode ended with
+    cur = order.copy()
+    for b in range(8):
+        if not syn[b].any():
+            continue
+        w = port_oracle.decode_batch(H, syn[b:b + 1], 0.07, serial_schedule_order=cur, **kw)
+        out = d.decode(syn[b])
+        assert np.array_equal(out, w[0][0]) and d.iter == int(w[2][0]) and d.converge == bool(w[1][0])
+        new = np.asarray(d.serial_schedule_order)
+        assert sorted(new.tolist()) == list(range(240))
+        cur = new

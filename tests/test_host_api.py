@@ -4,6 +4,7 @@ test_scipy_helpers.py), the C-ABI library's exports, and the host OSD-0 against 
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -285,6 +286,17 @@ def test_osd_column_order_is_the_libc_qsort_merge_tree(tmp_path):
     subprocess.run(["gcc", "-O2", "-o", exe, src], check=True)
     res = subprocess.run([exe, "3000"], capture_output=True, text=True)
     assert res.returncode == 0 and res.stdout.startswith("0 orders differ"), res.stdout
+
+
+def test_stl_sort_restatement_matches_libstdcxx(tmp_path):
+    """ldpc_b200/csrc/stl_sort.h (the std::sort restatement behind the SERIAL_RELATIVE schedule, bp.hpp:469-482)
+    against the real std::sort with the reference's comparator: random, tie-heavy, all-equal, NaN, sorted, reversed
+    and median-of-3-killer inputs, also re-sorting a previous result with new keys."""
+    exe = str(tmp_path / "stl_sort_check")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "stl_sort_check.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src], check=True)
+    res = subprocess.run([exe, "3000"], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.startswith("0 permutations differ"), res.stdout
 
 
 @pytest.mark.parametrize("mk", [lambda: codes.regular_ldpc(1000, 3, 6, seed=1), codes.bivariate_bicycle_144,

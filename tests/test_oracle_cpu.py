@@ -54,6 +54,17 @@ CASES = [
     ("bb144_ms", lambda: codes.bivariate_bicycle_144(), 0.02, 600,
      dict(max_iter=50, bp_method="ms", schedule="parallel", ms_scaling_factor=0.625)),
     ("hamming5_ps", lambda: codes.hamming_code(5), 0.1, 100, dict(max_iter=2, bp_method="ps", schedule="parallel")),
+    # SERIAL_RELATIVE (bp.hpp:469-482): the port restates libstdc++'s std::sort, ties and all
+    ("ldpc1000_ms_relative", lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, 60,
+     dict(max_iter=50, bp_method="ms", schedule="serial_relative", ms_scaling_factor=0.625)),
+    ("ldpc1000_ms_relative_adaptive_hard", lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.085, 30,
+     dict(max_iter=30, bp_method="ms", schedule="serial_relative", ms_scaling_factor=0.0)),
+    ("ldpc240_ps_relative", lambda: codes.regular_ldpc(240, 3, 6, seed=3), 0.06, 100,
+     dict(max_iter=30, bp_method="ps", schedule="serial_relative")),
+    ("surface13_ms_relative", lambda: codes.rotated_surface_code_x(13), 0.05, 200,
+     dict(max_iter=20, bp_method="ms", schedule="serial_relative", ms_scaling_factor=0.625)),
+    ("hamming5_ps_relative", lambda: codes.hamming_code(5), 0.1, 100,
+     dict(max_iter=5, bp_method="ps", schedule="serial_relative")),
 ]
 
 
