@@ -50,8 +50,8 @@ int ensure(bpb_decoder *h, bpb::DeviceBuffer &b, size_t bytes, bool zero = false
 }
 
 std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
-    return {&h->blob,     &h->order_d,   &h->counter,   &h->msg,        &h->dec_w,      &h->syn_w,    &h->llr_tile,
-            &h->packed,   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
+    return {&h->blob,     &h->order_d,   &h->counter_s[0], &h->counter_s[1],   &h->msg,        &h->dec_w,      &h->syn_w,    &h->llr_tile,
+            &h->packed_s[0], &h->packed_s[1],   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
             &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1],
             &h->st_bp[0],   &h->st_bp[1],   &h->osd_conv,  &h->mc_thresh, &h->mc_err, &h->mc_syn, &h->mc_dec,
             &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg, &h->pair_tab, &h->rel_order, &h->rel_order_out, &h->rel_msg};
@@ -305,8 +305,8 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     if ((rc = ensure(h, h->dec_w, warps * (size_t) n_pad * 4, true, st))) return rc;
     if ((rc = ensure(h, h->syn_w, p.smem_syn ? 16 : warps * (size_t) m_pad * 4, true, st))) return rc;
     if (llr && (rc = ensure(h, h->llr_tile, warps * (size_t) g.n * 32 * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->counter, 64))) return rc;
-    BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+    if ((rc = ensure(h, h->counter_s[h->slot], 64))) return rc;
+    BPB_CUDA(h, cudaMemsetAsync(h->counter_s[h->slot].ptr, 0, 64, st));
     // second stage for the ramp-down (parallel schedule, when the thread-group kernels can take the code)
     // second stage for the ramp-down: the thread-group kernels when they can take the code, else (parallel schedule,
     // messages beyond shared memory, e.g. n = 10^4) the edge-parallel kernel with its messages in an L2-resident scratch
@@ -315,9 +315,9 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     const bool second_stage = (stage2_smem || stage2_edge) && h->max_iter > 16 && !std::getenv("BPB_NO_SECOND_STAGE");
     if (second_stage && (rc = ensure(h, h->handoff, (size_t) warps * 32 * sizeof(uint32_t)))) return rc;
     p.iter_cap = second_stage ? 12 : h->max_iter + 1;
-    p.handoff_count = (unsigned long long *) h->counter.ptr + 1;
+    p.handoff_count = (unsigned long long *) h->counter_s[h->slot].ptr + 1;
     p.handoff_list = (uint32_t *) h->handoff.ptr;
-    p.iter_total = (unsigned long long *) h->counter.ptr + 3;
+    p.iter_total = (unsigned long long *) h->counter_s[h->slot].ptr + 3;
 
     p.blob = (const uint32_t *) h->blob.ptr;
     p.blob_words = h->blob_words;
@@ -334,7 +334,7 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     p.prior0 = h->prior.empty() ? 0.0 : h->prior[0];
     p.synd_packed = d_packed;
     p.batch = batch;
-    p.counter = (unsigned long long *) h->counter.ptr;
+    p.counter = (unsigned long long *) h->counter_s[h->slot].ptr;
     p.msg = (double *) h->msg.ptr;
     p.dec_w = (uint32_t *) h->dec_w.ptr;
     p.syn_w_g = (uint32_t *) h->syn_w.ptr;
@@ -357,9 +357,9 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     h->last_block = block;
     if (second_stage) {
         rc = stage2_smem ? launch_smem(h, d_packed, mwp, batch, d_dec, d_conv, d_iters, d_llr, st,
-                                       (const uint32_t *) h->handoff.ptr, (const unsigned long long *) h->counter.ptr + 1)
+                                       (const uint32_t *) h->handoff.ptr, (const unsigned long long *) h->counter_s[h->slot].ptr + 1)
                          : launch_edge(h, d_packed, mwp, batch, d_dec, d_conv, d_iters, d_llr, st,
-                                       (const uint32_t *) h->handoff.ptr, (const unsigned long long *) h->counter.ptr + 1);
+                                       (const uint32_t *) h->handoff.ptr, (const unsigned long long *) h->counter_s[h->slot].ptr + 1);
         if (rc) return rc;
         h->last_family = BPB_KERNEL_STREAM;
         h->last_grid = grid;
@@ -419,9 +419,9 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     int64_t grid64 = std::min<int64_t>(h->sm_count, (batch + G - 1) / G);
     if (grid64 < 1) grid64 = 1;
     int rc;
-    if ((rc = ensure(h, h->counter, 64))) return rc;
+    if ((rc = ensure(h, h->counter_s[h->slot], 64))) return rc;
     // counter words: [0] streaming queue, [1] hand-off count, [2] thread-group queue
-    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter_s[h->slot].ptr, 0, 64, st));
     if (index_list) grid64 = h->sm_count;  // the count lives on the device
     bpb::SmemParams p{};
     p.tab = (const uint32_t *) h->smem_tab.ptr;
@@ -455,7 +455,7 @@ int launch_smem(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.synd_packed = d_packed;
     p.mwp = mwp;
     p.batch = batch;
-    p.counter = (unsigned long long *) h->counter.ptr + 2;
+    p.counter = (unsigned long long *) h->counter_s[h->slot].ptr + 2;
     p.index_list = index_list;
     p.batch_dev = batch_dev;
     p.out_dec = d_dec;
@@ -536,9 +536,9 @@ int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     int64_t grid64 = std::min<int64_t>(h->sm_count, (batch + 2 * G - 1) / (2 * G));
     if (grid64 < 1) grid64 = 1;
     int rc;
-    if ((rc = ensure(h, h->counter, 64))) return rc;
+    if ((rc = ensure(h, h->counter_s[h->slot], 64))) return rc;
     // counter words: [0] streaming queue, [1] hand-off count, [2] thread-group queue
-    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter_s[h->slot].ptr, 0, 64, st));
     if (index_list) grid64 = h->sm_count;  // the count lives on the device
     bpb::PairParams p{};
     p.tab = (const uint32_t *) h->pair_tab.ptr;
@@ -569,7 +569,7 @@ int launch_pair(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.synd_packed = d_packed;
     p.mwp = mwp;
     p.batch = batch;
-    p.counter = (unsigned long long *) h->counter.ptr + 2;
+    p.counter = (unsigned long long *) h->counter_s[h->slot].ptr + 2;
     p.index_list = index_list;
     p.batch_dev = batch_dev;
     p.out_dec = d_dec;
@@ -641,8 +641,8 @@ int launch_edge(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     if (!index_list) grid64 = std::min<int64_t>(grid64, batch);
     if (grid64 < 1) grid64 = 1;
     int rc;
-    if ((rc = ensure(h, h->counter, 64))) return rc;
-    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+    if ((rc = ensure(h, h->counter_s[h->slot], 64))) return rc;
+    if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter_s[h->slot].ptr, 0, 64, st));
     if (msg_global && (rc = ensure(h, h->edge_msg, (size_t) grid64 * msg_bytes))) return rc;
     const uint32_t *blob = (const uint32_t *) h->blob.ptr;
     p.row_ptr = blob;
@@ -661,7 +661,7 @@ int launch_edge(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.synd_packed = d_packed;
     p.mwp = mwp;
     p.batch = batch;
-    p.counter = (unsigned long long *) h->counter.ptr + 2;  // word 2: the second-stage / thread-group queue
+    p.counter = (unsigned long long *) h->counter_s[h->slot].ptr + 2;  // word 2: the second-stage / thread-group queue
     p.index_list = index_list;
     p.batch_dev = batch_dev;
     p.msg_global = (double *) h->edge_msg.ptr;
@@ -760,6 +760,7 @@ int bpb_create(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *co
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
@@ -808,6 +809,7 @@ void bpb_destroy(bpb_decoder *h) {
         if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
     if (h->host_counts) cudaFreeHost(h->host_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
 }
 
@@ -990,16 +992,17 @@ int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, i
     }
     // The handle's workspaces (packed syndromes, counters, message tiles) are shared by consecutive calls: a call on
     // another stream waits for the previous call's work.
-    if (h->have_last && h->last_stream != st) BPB_CUDA(h, cudaStreamWaitEvent(st, h->ev_last, 0));
+    // (the dual-stream host pipeline gives each of its two streams its own counters / packed buffer instead)
+    if (h->have_last && h->last_stream != st && !h->pipeline_dual) BPB_CUDA(h, cudaStreamWaitEvent(st, h->ev_last, 0));
     const bpb::HostGraph &g = h->g;
     const int mwp = round_up((g.m + 31) / 32, 4);
     const uint32_t *d_packed = reinterpret_cast<const uint32_t *>(d_input);
     if (input_type != kInputPacked) {
-        if ((rc = ensure(h, h->packed, (size_t) batch * mwp * 4))) return rc;
-        d_packed = (const uint32_t *) h->packed.ptr;
+        if ((rc = ensure(h, h->packed_s[h->slot], (size_t) batch * mwp * 4))) return rc;
+        d_packed = (const uint32_t *) h->packed_s[h->slot].ptr;
     }
     h->last_packed = d_packed;
-    uint32_t *d_pack_out = (uint32_t *) h->packed.ptr;
+    uint32_t *d_pack_out = (uint32_t *) h->packed_s[h->slot].ptr;
     const int pgrid = (int) std::min<int64_t>((batch + 7) / 8, (int64_t) h->sm_count * 16);
     if (input_type == kInputPacked) {
     } else if (input_type == BPB_INPUT_SYNDROME) {
@@ -1018,14 +1021,14 @@ int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, i
                                    cudaMemcpyHostToDevice));
             h->order_dirty = false;
         }
-        if ((rc = ensure(h, h->counter, 64))) return rc;
-        BPB_CUDA(h, cudaMemsetAsync(h->counter.ptr, 0, 64, st));
+        if ((rc = ensure(h, h->counter_s[h->slot], 64))) return rc;
+        BPB_CUDA(h, cudaMemsetAsync(h->counter_s[h->slot].ptr, 0, 64, st));
         int grid = 0;
         BPB_CUDA(h, cudaEventRecord(h->kev0, st));
         const int e = bpb::launch_relative_kernel(g, h->sm_count, h->max_smem_optin, (const uint32_t *) h->blob.ptr,
                                                   h->prior_off, h->method, h->max_iter, h->ms_scaling,
                                                   (const uint32_t *) h->rel_order.ptr, (int) h->serial_order.size(),
-                                                  d_packed, mwp, batch, (unsigned long long *) h->counter.ptr + 2,
+                                                  d_packed, mwp, batch, (unsigned long long *) h->counter_s[h->slot].ptr + 2,
                                                   &h->rel_msg, d_decoding, d_converged, d_iterations, d_llr,
                                                   h->llr_last_only ? 1 : 0, (int32_t *) h->rel_order_out.ptr, st, &grid);
         if (e == -1) {
@@ -1241,9 +1244,24 @@ int host_pipeline(bpb_decoder *h, int input_type, const uint8_t *input, int64_t 
         if ((rc = ensure(h, h->osd_count, 64, true, h->stream))) return rc;
         PIPE_CUDA(cudaMemsetAsync((unsigned long long *) h->osd_count.ptr + 2, 0, 8, h->stream));
     }
+    // On-chip families keep no per-syndrome state in global memory, so the kernels of consecutive chunks may run
+    // concurrently: two compute streams (one per staging slot, each with its own work-queue counters and packed
+    // syndromes).  The CTAs of chunk c+1 start on the SMs that chunk c's CTAs leave, which hides the ramp-down of every
+    // chunk (the last syndromes of a chunk include 50-iteration non-convergers that would keep a few SMs busy and the
+    // rest idle for ~0.2 ms).  The streaming family shares its message tiles between launches and BP+OSD its failure
+    // lists: they stay on one stream.
+    const bool dual = smem_able && !with_osd && h->schedule == BPB_PARALLEL && h->kernel_pref != BPB_KERNEL_EDGE &&
+                      batch > (int64_t) h->sm_count * 2 && !std::getenv("BPB_NO_DUAL_STREAM");
+    if (dual && h->have_last) {
+        PIPE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_last, 0));
+        PIPE_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_last, 0));
+    }
+    h->pipeline_dual = dual;
     int64_t c = 0;
     for (int64_t lo = 0; lo < batch && rc == BPB_OK; lo += chunk_max, ++c) {
         const int s = (int) (c & 1);
+        const cudaStream_t cs = (dual && s) ? h->stream2 : h->stream;
+        h->slot = dual ? s : 0;
         const int64_t nb = std::min(chunk_max, batch - lo);
         if ((rc = ensure(h, h->st_in[s], cap * in_w))) break;
         if ((rc = ensure(h, h->st_dec[s], cap * g.n))) break;
@@ -1260,20 +1278,20 @@ int host_pipeline(bpb_decoder *h, int input_type, const uint8_t *input, int64_t 
         }
         PIPE_CUDA(cudaMemcpyAsync(h->st_in[s].ptr, src, (size_t) nb * in_w, cudaMemcpyHostToDevice, h->s_in));
         PIPE_CUDA(cudaEventRecord(h->ev_in[s], h->s_in));
-        PIPE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
-        if (c >= 2) PIPE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_out[s], 0));  // slot's outputs drained
+        PIPE_CUDA(cudaStreamWaitEvent(cs, h->ev_in[s], 0));
+        if (c >= 2) PIPE_CUDA(cudaStreamWaitEvent(cs, h->ev_out[s], 0));  // slot's outputs drained
         if (rc) break;
         if (with_osd)
             rc = enqueue_bposd_device(h, (const uint8_t *) h->st_in[s].ptr, nb, (uint8_t *) h->st_dec[s].ptr,
                                       (uint8_t *) h->st_conv[s].ptr, (int32_t *) h->st_iters[s].ptr,
-                                      bp_decoding ? (uint8_t *) h->st_bp[s].ptr : nullptr, h->stream);
+                                      bp_decoding ? (uint8_t *) h->st_bp[s].ptr : nullptr, cs);
         else
             rc = bpb_decode_batch_device(h, input_type, (const uint8_t *) h->st_in[s].ptr, nb,
                                          (uint8_t *) h->st_dec[s].ptr, (uint8_t *) h->st_conv[s].ptr,
                                          (int32_t *) h->st_iters[s].ptr, llr ? (double *) h->st_llr[s].ptr : nullptr,
-                                         h->stream);
+                                         cs);
         if (rc) break;
-        PIPE_CUDA(cudaEventRecord(h->ev_k[s], h->stream));
+        PIPE_CUDA(cudaEventRecord(h->ev_k[s], cs));
         PIPE_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_k[s], 0));
         PIPE_CUDA(cudaMemcpyAsync(decoding + lo * g.n, h->st_dec[s].ptr, (size_t) nb * g.n, cudaMemcpyDeviceToHost,
                                   h->s_out));
@@ -1294,6 +1312,13 @@ int host_pipeline(bpb_decoder *h, int input_type, const uint8_t *input, int64_t 
     // also on the error path: no copy into the caller's memory may be in flight when this returns
     cudaStreamSynchronize(h->s_in);
     cudaError_t e1 = cudaStreamSynchronize(h->stream);
+    if (dual) {
+        const cudaError_t e1b = cudaStreamSynchronize(h->stream2);
+        if (e1 == cudaSuccess) e1 = e1b;
+    }
+    h->pipeline_dual = false;
+    h->slot = 0;
+    h->have_last = false;  // everything this call enqueued has finished
     cudaError_t e2 = cudaStreamSynchronize(h->s_out);
     if (rc == BPB_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
         h->err = std::string("pipeline synchronise: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
@@ -1627,9 +1652,9 @@ int bpb_get_info(const bpb_decoder *h_, bpb_info *out) {
     int64_t ws = 0;
     for (bpb::DeviceBuffer *b: all_buffers(h)) ws += (int64_t) b->bytes;
     out->workspace_bytes = ws;
-    if (h->device >= 0 && h->counter.ptr && h->last_family == BPB_KERNEL_STREAM) {
+    if (h->device >= 0 && h->counter_s[h->slot].ptr && h->last_family == BPB_KERNEL_STREAM) {
         unsigned long long words[4] = {0, 0, 0, 0};
-        if (cudaMemcpy(words, h->counter.ptr, sizeof(words), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        if (cudaMemcpy(words, h->counter_s[h->slot].ptr, sizeof(words), cudaMemcpyDeviceToHost) == cudaSuccess) {
             out->stream_handed_off = (int64_t) words[1];
             out->stream_iterations = (int64_t) words[3];
         }

@@ -118,7 +118,13 @@ struct bpb_decoder {
     int kernel_pref = BPB_KERNEL_AUTO;
     // device state
     bool graph_dirty = true;  // blob must be (re)uploaded (prior or order changed)
-    bpb::DeviceBuffer blob, order_d, counter, msg, dec_w, syn_w, llr_tile, packed, smem_tab, handoff;
+    bpb::DeviceBuffer blob, order_d, msg, dec_w, syn_w, llr_tile, smem_tab, handoff;
+    // work-queue counters and bit-packed syndromes: one set per pipeline slot, so that the kernels of consecutive
+    // chunks of the host pipeline may overlap (on-chip families); everything else uses slot 0
+    bpb::DeviceBuffer counter_s[2], packed_s[2];
+    int slot = 0;
+    bool pipeline_dual = false;  // host_pipeline is alternating two compute streams
+    cudaStream_t stream2 = nullptr;
     bpb::DeviceBuffer osd_llr, osd_fail_llr, osd_fail_idx, osd_count;  // BP+OSD batch path
     bpb::OsdDevicePlan osd_plan;
     bpb::DeviceBuffer rel_order, rel_order_out, rel_msg;  // SERIAL_RELATIVE: configured / final schedule, scratch

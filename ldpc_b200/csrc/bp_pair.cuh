@@ -91,16 +91,25 @@ __global__ void __launch_bounds__(MAXT, 1) bp_pair_kernel(const PairParams p) {
     // as the syndrome, and a column XORs its checks in (bp.hpp:290-294) only when its decision FLIPS, so that
     // acc == syndrome ^ H x at the end of every bit pass.
     uint32_t xm = 0;
+    // The group leader always holds one syndrome claimed AHEAD in a register: the global atomic (and the index-list
+    // lookup of the second-stage use) is issued when a half retires but only consumed when the next half retires, so
+    // its latency never sits on the group's critical path.
+    auto claim_next = [&]() -> long long {
+        const long long claim = (long long) atomicAdd(p.counter, 1ull);
+        return (claim < limit) ? (p.index_list ? (long long) p.index_list[claim] : claim) : -1;
+    };
+    long long pend = -1;
+    if (t == 0) pend = claim_next();
     for (;;) {
         if (need0 || need1) {
             if (t == 0) {
                 if (need0) {
-                    const long long claim = (long long) atomicAdd(p.counter, 1ull);
-                    ctl[0] = (claim < limit) ? (p.index_list ? (long long) p.index_list[claim] : claim) : -1;
+                    ctl[0] = pend;
+                    pend = (pend >= 0) ? claim_next() : -1;
                 }
                 if (need1) {
-                    const long long claim = (long long) atomicAdd(p.counter, 1ull);
-                    ctl[1] = (claim < limit) ? (p.index_list ? (long long) p.index_list[claim] : claim) : -1;
+                    ctl[1] = pend;
+                    pend = (pend >= 0) ? claim_next() : -1;
                 }
             }
             group_sync(bar, T);
