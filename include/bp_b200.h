@@ -164,6 +164,13 @@ void bpb_host_free(void *p);
 
 const char *bpb_version(void);
 
+/* Product-sum bit-exactness depends on the host the REFERENCE runs on: the device evaluates std::tanh / std::log
+ * (bp.hpp:208,216) the way glibc 2.39's x86-64 FMA variants do (ldpc_b200/csrc/ref_libm.h).  This host-side check
+ * evaluates that restatement over `samples` deterministic arguments and returns how many results differ from the live
+ * libm: 0 on such a host; non-zero means product-sum LLRs agree with a reference run on THIS host to ~1 ulp per
+ * operation (well inside 1e-5) rather than bit for bit.  No device work. */
+int bpb_libm_selfcheck(int samples);
+
 #ifdef __cplusplus
 }
 #endif

@@ -204,18 +204,40 @@ int upload_graph(bpb_decoder *h) {
     h->serial_batches = build_serial_batches(g, h->serial_order, sb);
     std::vector<uint32_t> upload = h->serial_batches;
     h->serial_entries = (int) h->serial_batches.size();
-    if (g.regular && g.max_row_degree == 6 && g.max_col_degree == 3 && g.m < (1 << 28)) {
-        // regular-code serial program (see bp_stream.cuh): {j, row | self << 28 for each of the three edges}
+    h->serial_program_flags = false;
+    if (g.regular && g.max_row_degree == 6 && g.max_col_degree == 3 && g.m < (1 << 20)) {
+        // regular-code serial program (see bp_stream.cuh): {j, w_k for each of the three edges}, w_k = row | visited
+        // flags << 20 | self << 28.  Flag f of an edge says that the f-th OTHER edge of its row belongs to a bit that
+        // comes earlier in the program, i.e. has already been rewritten in the current sweep (levelisation keeps the
+        // relative order of bits that share a check, so program order = reference order for that question).
         upload.assign(h->serial_batches.size() * 4, 0xffffffffu);
+        std::vector<int> pos_of_bit((size_t) g.n, -1);
+        bool covers_once = true;  // every bit at most once in the schedule (the flags assume it)
+        for (size_t q = 0; q < h->serial_batches.size(); q++) {
+            const uint32_t j = h->serial_batches[q];
+            if (j == 0xffffffffu) continue;
+            if (pos_of_bit[j] >= 0) covers_once = false;
+            pos_of_bit[j] = (int) q;
+        }
+        for (int j = 0; j < g.n; j++)
+            if (pos_of_bit[(size_t) j] < 0) covers_once = false;  // an unvisited bit keeps its prior for ever
         for (size_t q = 0; q < h->serial_batches.size(); q++) {
             const uint32_t j = h->serial_batches[q];
             if (j == 0xffffffffu) continue;
             upload[4 * q] = j;
             for (uint32_t e = g.col_ptr[j]; e < g.col_ptr[j + 1]; e++) {
                 const uint32_t i = g.row_idx[e], self = g.csc2csr[e] - g.row_ptr[i];
-                upload[4 * q + 1 + (e - g.col_ptr[j])] = i | (self << 28);
+                uint32_t flags = 0;
+                int f = 0;
+                for (uint32_t r = g.row_ptr[i]; r < g.row_ptr[i + 1]; r++) {
+                    if (r == g.csc2csr[e]) continue;
+                    if (pos_of_bit[g.col_idx[r]] >= 0 && pos_of_bit[g.col_idx[r]] < (int) q) flags |= 1u << f;
+                    f++;
+                }
+                upload[4 * q + 1 + (e - g.col_ptr[j])] = i | (flags << 20) | (self << 28);
             }
         }
+        h->serial_program_flags = covers_once;
     }
     rc = ensure(h, h->order_d, upload.size() * sizeof(uint32_t));
     if (rc) return rc;
@@ -346,6 +368,8 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     p.order = (const uint32_t *) h->order_d.ptr;
     p.order_len = h->serial_entries;
     p.llr_last_only = h->llr_last_only ? 1 : 0;
+    p.no_compaction = std::getenv("BPB_NO_COMPACTION") ? 1 : 0;
+    p.serial_no_init = (h->serial_program_flags && h->uniform_prior && !std::getenv("BPB_SERIAL_INIT")) ? 1 : 0;
     BPB_CUDA(h, cudaEventRecord(h->kev0, st));
     k<<<grid, block, smem_bytes, st>>>(p);
     BPB_CUDA(h, cudaGetLastError());
@@ -711,7 +735,9 @@ int check_ready(bpb_decoder *h) {
 // ======================================================================================================
 extern "C" {
 
-const char *bpb_version(void) { return "ldpc_b200 0.1 (sm_100a)"; }
+const char *bpb_version(void) { return "ldpc_b200 0.2 (sm_100a)"; }
+
+int bpb_libm_selfcheck(int samples) { return bpb::libm_selfcheck(samples > 0 ? samples : 20000); }
 
 const char *bpb_last_error(const bpb_decoder *h) {
     if (h) return h->err.c_str();
@@ -1073,11 +1099,14 @@ int decode_device_core(bpb_decoder *h, int input_type, const uint8_t *d_input, i
         h->err = "kernel family 'edge' serves the parallel schedule with degrees <= 32 only";
         return BPB_ERR_UNSUPPORTED;
     }
-    // AUTO, parallel schedule, a batch too small to give every SM a thread group's worth of work: one CTA per
-    // syndrome with a lane per edge has the lower latency (latency table)
+    // AUTO, parallel schedule, small batch, a code the on-chip families cannot hold: one CTA per syndrome with a lane
+    // per edge and L2-resident messages instead of a streaming-kernel launch that would leave the lanes of every warp
+    // but one idle.  (For codes that do fit, the thread-group kernels are faster at every batch size, also for a
+    // single syndrome: 44 vs 89 us at n = 1000, profiles/r2_latency_c2.jsonl.)
     const bool small_batch = batch <= (int64_t) h->sm_count * 2;
     const bool use_edge = h->kernel_pref == BPB_KERNEL_EDGE ||
-                          (h->kernel_pref == BPB_KERNEL_AUTO && edge_able(h) && small_batch && !std::getenv("BPB_NO_EDGE_AUTO"));
+                          (h->kernel_pref == BPB_KERNEL_AUTO && edge_able(h) && small_batch && !smem_able &&
+                           !pair_able(h) && !std::getenv("BPB_NO_EDGE_AUTO"));
     if (h->kernel_pref == BPB_KERNEL_PAIR && !pair_able(h)) {
         h->err = "kernel family 'pair' serves the parallel schedule of codes whose messages fit in shared memory twice: " +
                  h->pair_plan.why;

@@ -96,6 +96,7 @@ void compute_priors(bpb_decoder *h);
 std::vector<uint32_t> build_serial_batches(const HostGraph &g, const std::vector<uint32_t> &order, int sb);
 void build_smem_plan(bpb_decoder *h);
 void build_pair_plan(bpb_decoder *h);
+int libm_selfcheck(int samples);
 int place_messages(const HostGraph &g, int lanes_per_phase, std::vector<uint32_t> &slot_of_edge);
 }  // namespace bpb
 
@@ -115,6 +116,7 @@ struct bpb_decoder {
     std::vector<uint32_t> serial_order;
     std::vector<uint32_t> serial_batches;  // levelised, padded schedule the serial kernels consume
     int serial_entries = 0;                // number of schedule entries (bits + padding)
+    bool serial_program_flags = false;     // the regular-code serial program carries the "already visited" flags
     int kernel_pref = BPB_KERNEL_AUTO;
     // device state
     bool graph_dirty = true;  // blob must be (re)uploaded (prior or order changed)

@@ -10,8 +10,39 @@
 #include <cstring>
 
 #include "bp_decoder.h"
+#include "ref_libm.h"
 
 namespace bpb {
+
+// The product-sum kernels evaluate tanh / log with ref_libm.h, a restatement of glibc 2.39's x86-64 FMA variants, so
+// that their messages are the doubles the reference computes on such a host.  On a host whose libm is a different
+// one (another glibc, no FMA) the reference itself computes different last bits; this check says so instead of letting
+// "bit-exact" silently become "within 1e-5": it evaluates the restatement on the host over a deterministic sample
+// (near 1, tiny, large, the tanh -> atanh chain of bp.hpp:208-217) and counts disagreements with the live libm.
+int libm_selfcheck(int samples) {
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() {
+        s ^= s << 13;
+        s ^= s >> 7;
+        s ^= s << 17;
+        return s;
+    };
+    auto uni = [&](double lo, double hi) { return lo + (hi - lo) * ((double) (rnd() >> 11) * 0x1p-53); };
+    auto same = [](double a, double b) { return std::memcmp(&a, &b, 8) == 0 || (a != a && b != b); };
+    int bad = 0;
+    for (int i = 0; i < samples; i++) {
+        const double xs[5] = {uni(0.0, 4.0), std::exp(uni(-700.0, 700.0)), uni(0.9, 1.1), uni(-45.0, 45.0),
+                              uni(-2.2, 2.2)};
+        for (double x: xs) {
+            if (!same(rl_log(x), std::log(x))) bad++;
+            if (!same(rl_tanh(x), std::tanh(x))) bad++;
+        }
+        const double b1 = uni(-40, 40), b2 = uni(-6, 6);
+        const double c1 = std::tanh(b1 / 2) * std::tanh(b2 / 2), c2 = rl_tanh(b1 / 2) * rl_tanh(b2 / 2);
+        if (!same(std::log((1 + c1) / (1 - c1)), rl_log((1 + c2) / (1 - c2)))) bad++;
+    }
+    return bad;
+}
 
 void compute_priors(bpb_decoder *h) {
     const bpb::HostGraph &g = h->g;

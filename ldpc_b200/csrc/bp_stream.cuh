@@ -37,7 +37,7 @@ template <int METHOD, int SCHED, int DC, int DV, bool LLR, bool UNI>
 #ifndef BPB_SERIAL_MINBLOCKS
 #define BPB_SERIAL_MINBLOCKS 1
 #endif
-__global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParallel ? 2 : BPB_SERIAL_MINBLOCKS) : 1)
+__global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? ((SCHED == kParallel || UNI) ? 2 : BPB_SERIAL_MINBLOCKS) : 1)
     bp_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31;
@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParalle
                     const int i = w * 32 + lane;
                     if (i < m) syn_w[i] = (syn_w[i] & ~newmask) | (mine_w & newmask);
                 }
-                if (SCHED == kSerial || GEN) {
-                    // explicit initialise_log_domain_bp (bp.hpp:147-157) for the new lanes
+                if ((SCHED == kSerial && !p.serial_no_init) || GEN) {
+                    // explicit initialise_log_domain_bp (bp.hpp:147-157) for the new lanes.  A lone fresh lane writes
+                    // 8 bytes of a 32-byte sector: the memory system turns that into a sector read + a sector write,
+                    // 8x the payload, which is why the regular-code serial program avoids it (serial_no_init below)
                     if (fresh)
                         for (int e = 0; e < nnz; ++e)
                             st_msg(tile + (size_t) e * 32, p.uniform_prior ? p.prior0 : prior[col_idx[e]]);
@@ -344,12 +346,14 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParalle
             constexpr int SB = SerialBatch<DC, DV, UNI>::v;
             if (UNI) {
                 // Regular codes: the host compiles the levelised schedule into a program of one 128-bit word per
-                // (bit, padding included): {j, w_0, w_1, w_2,...}, w_k = row index | self position << 28, so the
+                // (bit, padding included): {j, w_0, w_1, w_2,...}, w_k = row index (20 bits) | "the f-th other edge of the
+                // row was already visited in this sweep" (bit 20 + f) | self position << 28, so the
                 // only dependent step between the (sequential, warp-uniform) program fetch and the message loads
                 // is address arithmetic.  Of a row's DC contiguous messages the DC-1 that are not the bit's own
                 // are loaded: offset f + (f >= self).
                 static_assert(!UNI || DV <= 3, "program word layout holds three edges");
                 const uint4 *prog = reinterpret_cast<const uint4 *>(p.order);
+                const bool fresh_flags = p.serial_no_init != 0;
                 for (int o0 = 0; o0 < p.order_len; o0 += SB) {
                     uint4 pw[SB];
                     double bv[SB][DV][DC - 1];
@@ -360,12 +364,16 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParalle
                         const uint32_t wk[3] = {pw[q].y, pw[q].z, pw[q].w};
 #pragma unroll
                         for (int k = 0; k < DV; ++k) {
-                            const uint32_t rb = (wk[k] & 0x0fffffffu) * DC, sp = wk[k] >> 28;
+                            const uint32_t rb = (wk[k] & kProgRowMask) * DC, sp = wk[k] >> 28;
 #pragma unroll
                             for (int f = 0; f < DC - 1; ++f) {
-                                double v = 0.0;
-                                if (active && pw[q].x != 0xffffffffu)
-                                    v = ld_msg(tile + (size_t) (rb + f + (f >= (int) sp ? 1 : 0)) * 32);
+                                // In a syndrome's first iteration a neighbour that has not been visited yet still holds
+                                // its prior (bp.hpp:147-157 set every message to it): the program says which ones have
+                                // (bit 20+f), so nothing is initialised in memory and nothing stale is read.
+                                const uint32_t e = rb + f + (f >= (int) sp ? 1 : 0);
+                                const bool written = !(fresh_flags && first) || ((wk[k] >> (20 + f)) & 1u);
+                                double v = p.prior0;  // serial_no_init is only set for a uniform prior
+                                if (active && pw[q].x != 0xffffffffu && written) v = ld_msg(tile + (size_t) e * 32);
                                 bv[q][k][f] = v;
                             }
                         }
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParalle
                         double c[DV];
 #pragma unroll
                         for (int k = 0; k < DV; ++k) {
-                            const uint32_t i = wk[k] & 0x0fffffffu;
+                            const uint32_t i = wk[k] & kProgRowMask;
                             const uint32_t s = (syn_w[i] >> lane) & 1u;
                             if (METHOD == kMinimumSum) {
                                 uint32_t sg = s;  // bp.hpp:503-519
@@ -405,7 +413,7 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParalle
                         if (lane == 0) dec_w[j] = W;
 #pragma unroll
                         for (int k = 0; k < DV; ++k) {
-                            const uint32_t e = (wk[k] & 0x0fffffffu) * DC + (wk[k] >> 28);
+                            const uint32_t e = (wk[k] & kProgRowMask) * DC + (wk[k] >> 28);
                             if (active) st_msg(tile + (size_t) e * 32, c[k]);
                         }
                     }
@@ -552,6 +560,52 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? (SCHED == kParalle
         if (done || defer) {
             atomicAdd(p.iter_total, (unsigned long long) it);  // iterations this kernel really executed (roofline)
             idx = -1;
+        }
+
+        // ---------------- ramp-down: compact the live lanes of the warp ---------------------------------
+        // Once the queue is empty, lanes that finish leave holes.  A message row of the tile is 8 DRAM sectors of 4
+        // lanes each, and a sector with one live lane is fetched and written whole: ncu at n = 10^4 shows the memory
+        // system saturated during the ramp-down while a third of its traffic is dead lanes.  When the live lanes
+        // would fit in at most half of the sectors they occupy, move them to lanes 0..k-1: per-lane registers and the
+        // syndrome ballot words by shuffle / bit permutation, the message columns by one read + one write of the tile
+        // (a third of a serial-schedule iteration).  Warp-local and exact: only where a syndrome's state lives changes.
+        if (exhausted && !p.no_compaction) {
+            const uint32_t live = __ballot_sync(0xffffffffu, idx >= 0);
+            const int k = __popc(live);
+            uint32_t quads = live | (live >> 1) | (live >> 2) | (live >> 3);
+            quads &= 0x11111111u;
+            const int occupied = __popc(quads);
+            if (k > 0 && ((k + 3) >> 2) * 2 <= occupied) {
+                const bool was_live = idx >= 0;
+                const int src = (lane < k) ? (int) __fns(live, 0, lane + 1) : lane;  // old lane of new lane `lane`
+                const long long nidx = __shfl_sync(0xffffffffu, idx, src);
+                const int nit = __shfl_sync(0xffffffffu, it, src);
+                idx = (lane < k) ? nidx : -1;
+                it = (lane < k) ? nit : 0;
+                for (int i0 = 0; i0 < p.m_pad; i0 += 32) {
+                    const uint32_t w = syn_w[i0 + lane];
+                    uint32_t nw = 0;
+                    for (int q = 0; q < k; ++q) {
+                        const int sq = __shfl_sync(0xffffffffu, src, q);
+                        nw |= ((w >> sq) & 1u) << q;
+                    }
+                    syn_w[i0 + lane] = nw;
+                }
+                constexpr int U = 8;
+                const int words = nnz * (GEN ? 2 : 1);  // the generic kernel keeps c2b right behind b2c
+                for (int e0 = 0; e0 < words; e0 += U) {
+                    double v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        v[u] = (was_live && e0 + u < words) ? ld_msg(tile + (size_t) (e0 + u) * 32) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const double nv = __shfl_sync(0xffffffffu, v[u], src);
+                        if (lane < k && e0 + u < words) st_msg(tile + (size_t) (e0 + u) * 32, nv);
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
 }

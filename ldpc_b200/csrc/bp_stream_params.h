@@ -34,11 +34,15 @@ struct StreamParams {
     unsigned long long *handoff_count;  // number of syndromes handed to the second stage
     uint32_t *handoff_list;             // their batch indices
     unsigned long long *iter_total;     // sum of iterations executed by this launch
+    int serial_no_init;   // regular-code serial program carries the visited flags: no message initialisation in memory
+    int no_compaction;    // tuning / testing: keep live lanes where they are during the ramp-down
     int smem_graph, smem_syn;
     uint32_t smem_syn_off;  // word offset of the per-warp syndrome words in dynamic shared memory
 };
 
 using StreamKernel = void (*)(const StreamParams);
+
+constexpr uint32_t kProgRowMask = 0x000fffffu;  // serial program word: row index in the low 20 bits
 
 // Bits of one level the serial-schedule kernel keeps in flight together (host pads the schedule to this).
 #ifndef BPB_SERIAL_SB_UNI

@@ -10,16 +10,17 @@
  * Parity pinning: this restatement is checked bit-for-bit (decoding, converge,
  * iterations and every posterior-LLR bit pattern) against
  *   (1) the reference's own C++ compiled in place into oracle/_ref/libref_bp.so
- *       (oracle/ref_wrap.cpp, tests/test_oracle_vs_ref.py), and
+ *       (oracle/ref_wrap.cpp, tests/test_oracle_cpu.py::test_port_bit_identical_to_reference), and
  *   (2) the reference's known-answer tests (cpp_test/TestBPDecoder.cpp:122-344,
- *       python_test/test_bp_decoder.py:175-235) restated in tests/test_oracle_kat.py,
+ *       python_test/test_bp_decoder.py:175-235) restated in tests/kat.py (tests/test_oracle_cpu.py),
  *   (3) the committed fixtures tests/golden/*.npz generated from (1).
  *
  * What is restated (all arithmetic IEEE-754 binary64, evaluation order preserved):
  *   - initialise_log_domain_bp            src_cpp/bp.hpp:147-157
  *   - decode dispatch / received vector   src_cpp/bp.hpp:159-190
  *   - bp_decode_parallel  (PS + MS)       src_cpp/bp.hpp:192-325
- *   - bp_decode_serial    (PS + MS)       src_cpp/bp.hpp:451-545
+ *   - bp_decode_serial    (PS + MS)       src_cpp/bp.hpp:451-545, incl. the SERIAL_RELATIVE re-sort (:469-482) with
+ *     libstdc++'s std::sort restated
  *   - GF2Sparse::mulvec                   src_cpp/gf2sparse.hpp:177-214
  *   - traversal order: rows by ascending column, columns by ascending row, because
  *     insert_entry keeps both lists sorted (src_cpp/sparse_matrix_base.hpp:423-482).

@@ -30,7 +30,7 @@ for B in (1, 8, 32, 148, 296, 1024, 4096, 16384):
     d_conv = torch.empty(B, dtype=torch.uint8, device=dev)
     d_its = torch.empty(B, dtype=torch.int32, device=dev)
     row = {"config": cfg, "batch": B}
-    for fam in ("smem", "stream", "edge"):
+    for fam in ("pair", "smem", "stream", "edge"):
         d = BpDecoder(H, error_rate=p, input_vector_type="syndrome", kernel=fam, **kw)
         h = d._ensure_handle()
 
@@ -56,7 +56,7 @@ for B in (1, 8, 32, 148, 296, 1024, 4096, 16384):
     rows.append(row)
     print(json.dumps(row), flush=True)
 # single .decode() through the Python class (host call, includes H2D/D2H and the launch overheads)
-for fam in ("auto", "smem", "edge"):
+for fam in ("auto", "pair", "edge"):
     d = BpDecoder(H, error_rate=p, input_vector_type="syndrome", kernel=fam, **kw)
     syn = codes.bsc_syndromes(H, p, 64, seed=6)
     syn = syn[syn.any(axis=1)]
