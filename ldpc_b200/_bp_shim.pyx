@@ -60,6 +60,9 @@ cdef extern from "bp_b200.h":
     int bpb_set_osd_location(bpb_decoder *h, int v) nogil
     int bpb_set_devices(bpb_decoder *h, const int *ids, int count) nogil
     int bpb_get_last_schedule_order(bpb_decoder *h, int32_t *out, int len) nogil
+    int bpb_set_observables(bpb_decoder *h, int k, int64_t nnz, const int32_t *rows, const int32_t *cols) nogil
+    int bpb_decode_batch_b8(bpb_decoder *h, int with_osd, const uint8_t *syn, int64_t batch, uint8_t *dec,
+                            uint8_t *obs, uint8_t *conv, int32_t *its) nogil
     int bpb_set_serial_schedule_order(bpb_decoder *h, const int32_t *order, int len) nogil
     int bpb_mc_bsc(bpb_decoder *h, uint64_t seed, int64_t first_run, int64_t runs, const double *flip_prob,
                    int with_osd, int64_t *counts) nogil
@@ -134,6 +137,29 @@ cdef class NativeHandle:
 
     def set_osd_location(self, int v):
         self._check(bpb_set_osd_location(self.h, v))
+
+    def set_observables(self, int k, const int32_t[::1] rows, const int32_t[::1] cols):
+        cdef int rc
+        cdef int64_t nnz = rows.shape[0]
+        cdef const int32_t *r = &rows[0] if nnz else NULL
+        cdef const int32_t *c = &cols[0] if nnz else NULL
+        with nogil:
+            rc = bpb_set_observables(self.h, k, nnz, r, c)
+        self._check(rc)
+
+    def decode_batch_b8(self, int with_osd, const uint8_t[:, ::1] syn, uint8_t[:, ::1] dec, uint8_t[:, ::1] obs,
+                        uint8_t[::1] conv, int32_t[::1] its):
+        cdef int rc
+        cdef int64_t B = syn.shape[0]
+        if B == 0:
+            return
+        cdef uint8_t *pd = &dec[0, 0] if dec is not None else NULL
+        cdef uint8_t *po = &obs[0, 0] if obs is not None else NULL
+        cdef uint8_t *pc = &conv[0] if conv is not None else NULL
+        cdef int32_t *pi = &its[0] if its is not None else NULL
+        with nogil:
+            rc = bpb_decode_batch_b8(self.h, with_osd, &syn[0, 0], B, pd, po, pc, pi)
+        self._check(rc)
 
     def last_schedule_order(self, int32_t[::1] out):
         cdef int rc

@@ -99,6 +99,22 @@ class Handle:
             return self._wrap(self._nh.set_osd_location, int(where))
         _capi.check(self._ct, _capi.lib().bpb_set_osd_location(self._ct, int(where)))
 
+    def set_observables(self, k, rows, cols):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        if self._nh is not None:
+            return self._wrap(self._nh.set_observables, int(k), rows, cols)
+        _capi.check(self._ct, _capi.lib().bpb_set_observables(self._ct, int(k), rows.size, rows.ctypes.data_as(_capi._i32p),
+                                                               cols.ctypes.data_as(_capi._i32p)))
+
+    def decode_batch_b8(self, with_osd, syn, dec, obs, conv, its):
+        if self._nh is not None:
+            return self._wrap(self._nh.decode_batch_b8, int(with_osd), syn, dec, obs, conv, its)
+        rc = _capi.lib().bpb_decode_batch_b8(self._ct, int(with_osd), _capi.host_ptr(syn), syn.shape[0],
+                                             _capi.host_ptr(dec), _capi.host_ptr(obs), _capi.host_ptr(conv),
+                                             _capi.host_ptr(its))
+        _capi.check(self._ct, rc)
+
     def last_schedule_order(self, n):
         """SERIAL_RELATIVE: the schedule the last syndrome of the last decode call ended with."""
         out = np.empty(n, dtype=np.int32)

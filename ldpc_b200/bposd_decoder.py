@@ -113,6 +113,12 @@ class BpOsdDecoder(BpDecoderBase):
             self._osdw_decoding = dec[0].copy()
         return dec[0].astype(dtype)
 
+    @property
+    def _b8_with_osd(self) -> bool:  # decode_batch_b8 (BpDecoderBase): BP + OSD-0 on the device
+        if self._osd_method != OSD_OFF and self._osd_order != 0:
+            raise NotImplementedError("only OSD-0 (osd_order == 0) is implemented; OSD_E / OSD_CS are out of scope")
+        return self._osd_method != OSD_OFF
+
     def decode_batch(self, syndromes: np.ndarray, return_bp_decoding: bool = False) -> np.ndarray:
         """Decode ``[B, m]`` syndromes: BP for all on the GPU, then OSD-0 for the non-converged rows (on the device when
         the code fits the elimination kernel, else on the host).  ``return_bp_decoding`` also keeps the raw BP output

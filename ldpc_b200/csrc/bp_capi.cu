@@ -54,7 +54,9 @@ std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
             &h->packed_s[0], &h->packed_s[1],   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
             &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1],
             &h->st_bp[0],   &h->st_bp[1],   &h->osd_conv,  &h->mc_thresh, &h->mc_err, &h->mc_syn, &h->mc_dec,
-            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg, &h->pair_tab, &h->rel_order, &h->rel_order_out, &h->rel_msg};
+            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg, &h->pair_tab, &h->rel_order, &h->rel_order_out, &h->rel_msg, &h->obs_tab,
+            &h->b8_in[0], &h->b8_in[1], &h->b8_words[0], &h->b8_words[1], &h->b8_out[0], &h->b8_out[1],
+            &h->b8_obs[0], &h->b8_obs[1]};
 }
 
 void release(bpb::DeviceBuffer &b) {
@@ -110,6 +112,70 @@ __global__ void xor_received_kernel(uint8_t *__restrict__ dec, const uint8_t *__
     const long long stride = (long long) gridDim.x * blockDim.x;
     for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
         dec[i] ^= (v[i] != 0);
+}
+
+// ---- bit-packed I/O (stim's b8 layout: a row is ceil(bits / 8) bytes, bit k of the row is bit k % 8 of byte k / 8) ----
+
+// b8 syndrome rows -> the kernels' packed words [B][mwp] (same bit order; the row stride changes and bits >= m are
+// cleared: the convergence test looks at whole words)
+__global__ void unpack_b8_rows_kernel(const uint8_t *__restrict__ in, long long batch, int m, int mb, int mwp,
+                                      uint32_t *__restrict__ out) {
+    const long long total = batch * mwp;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const long long b = t / mwp;
+        const int w = (int) (t - b * mwp);
+        const uint8_t *row = in + b * mb;
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int byte = 4 * w + k;
+            if (byte < mb) v |= (uint32_t) row[byte] << (8 * k);
+        }
+        const int first_bit = 32 * w;
+        if (first_bit + 32 > m) v &= (first_bit >= m) ? 0u : ((1u << (m - first_bit)) - 1u);
+        out[t] = v;
+    }
+}
+
+// hard decisions [B][n] u8 -> b8 rows [B][ceil(n/8)]
+__global__ void pack_b8_rows_kernel(const uint8_t *__restrict__ dec, long long batch, int n, int nb,
+                                    uint8_t *__restrict__ out) {
+    const long long total = batch * nb;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const long long b = t / nb;
+        const int byte = (int) (t - b * nb);
+        const uint8_t *row = dec + b * n + 8 * byte;
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (8 * byte + k < n) v |= (uint32_t) (row[k] & 1u) << k;
+        out[t] = (uint8_t) v;
+    }
+}
+
+// predicted observable flips: obs = O x mod 2 for every row x of the decisions (what the reference's sinter driver
+// computes per shot on the host, sinter_bposd_decoder.py:121-124), b8 rows [B][ceil(k/8)]
+__global__ void observables_b8_kernel(const uint8_t *__restrict__ dec, long long batch, int n, int k, int kb,
+                                      const uint32_t *__restrict__ obs_ptr, const uint32_t *__restrict__ obs_col,
+                                      uint8_t *__restrict__ out) {
+    const long long total = batch * kb;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const long long b = t / kb;
+        const int byte = (int) (t - b * kb);
+        const uint8_t *row = dec + b * n;
+        uint32_t v = 0;
+        for (int q = 0; q < 8; ++q) {
+            const int o = 8 * byte + q;
+            if (o >= k) break;
+            uint32_t par = 0;
+            for (uint32_t e = obs_ptr[o]; e < obs_ptr[o + 1]; ++e) par ^= row[obs_col[e]];
+            v |= (par & 1u) << q;
+        }
+        out[t] = (uint8_t) v;
+    }
 }
 
 using bpb::build_serial_batches;
@@ -1498,6 +1564,183 @@ int bpb_bposd_decode_batch_device(bpb_decoder *h, const uint8_t *d_syndromes, in
     }
     return enqueue_bposd_device(h, d_syndromes, batch, d_decoding, d_converged, d_iterations, d_bp_decoding,
                                 (cudaStream_t) cuda_stream);
+}
+
+int bpb_set_observables(bpb_decoder *h, int k, int64_t nnz, const int32_t *rows, const int32_t *cols) {
+    if (!h) return BPB_ERR_ARG;
+    if (k < 0 || nnz < 0 || (nnz > 0 && (!rows || !cols))) {
+        h->err = "bad observables matrix";
+        return BPB_ERR_ARG;
+    }
+    std::vector<uint32_t> ptr((size_t) k + 1, 0u), col((size_t) nnz);
+    for (int64_t e = 0; e < nnz; e++) {
+        if (rows[e] < 0 || rows[e] >= k || cols[e] < 0 || cols[e] >= h->g.n) {
+            h->err = "observables matrix entry out of range";
+            return BPB_ERR_ARG;
+        }
+        ptr[(size_t) rows[e] + 1]++;
+    }
+    for (int o = 0; o < k; o++) ptr[(size_t) o + 1] += ptr[(size_t) o];
+    std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t e = 0; e < nnz; e++) col[fill[(size_t) rows[e]]++] = (uint32_t) cols[e];
+    h->obs_k = k;
+    h->obs_ptr = ptr;
+    h->obs_col = col;
+    h->obs_dirty = true;
+    for (bpb_decoder *c: h->children) {
+        const int rc_c = bpb_set_observables(c, k, nnz, rows, cols);
+        if (rc_c) {
+            h->err = c->err;
+            return rc_c;
+        }
+    }
+    return BPB_OK;
+}
+
+int bpb_decode_batch_b8(bpb_decoder *h, int with_osd, const uint8_t *syndromes_b8, int64_t batch, uint8_t *decoding_b8,
+                        uint8_t *observables_b8, uint8_t *converged, int32_t *iterations) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (batch < 0 || (batch > 0 && (!syndromes_b8 || (!decoding_b8 && !observables_b8)))) {
+        h->err = "bad decode arguments";
+        return BPB_ERR_ARG;
+    }
+    if (observables_b8 && h->obs_k <= 0) {
+        h->err = "observables requested but bpb_set_observables has not been called";
+        return BPB_ERR_ARG;
+    }
+    if (batch == 0) return BPB_OK;
+    const bpb::HostGraph &g = h->g;
+    const int mb = (g.m + 7) / 8, nb8 = (g.n + 7) / 8, kb = (h->obs_k + 7) / 8;
+    if (!h->children.empty()) {
+        // contiguous slices of the shots, one host thread per device
+        const int k = (int) h->children.size();
+        std::vector<int> rcs((size_t) k, BPB_OK);
+        auto work = [&](int r) {
+            const int64_t lo = batch * r / k, hi = batch * (r + 1) / k;
+            if (hi > lo)
+                rcs[(size_t) r] = bpb_decode_batch_b8(h->children[(size_t) r], with_osd, syndromes_b8 + lo * mb, hi - lo,
+                                                      decoding_b8 ? decoding_b8 + lo * nb8 : nullptr,
+                                                      observables_b8 ? observables_b8 + lo * kb : nullptr,
+                                                      converged ? converged + lo : nullptr,
+                                                      iterations ? iterations + lo : nullptr);
+        };
+        std::vector<std::thread> pool;
+        for (int r = 1; r < k; r++) pool.emplace_back(work, r);
+        work(0);
+        for (auto &t: pool) t.join();
+        for (int r = 0; r < k; r++)
+            if (rcs[(size_t) r]) {
+                h->err = "device slice " + std::to_string(r) + ": " + h->children[(size_t) r]->err;
+                return rcs[(size_t) r];
+            }
+        return BPB_OK;
+    }
+    BPB_CUDA(h, cudaSetDevice(h->device));
+    if (h->graph_dirty && (rc = upload_graph(h))) return rc;
+    if (with_osd && !osd_on_device(h)) {
+        h->err = "bpb_decode_batch_b8 with OSD-0 needs the device OSD-0 kernel, which is not available for this code";
+        return BPB_ERR_UNSUPPORTED;
+    }
+    if (observables_b8 && h->obs_dirty) {
+        const size_t words = h->obs_ptr.size() + h->obs_col.size();
+        if ((rc = ensure(h, h->obs_tab, words * 4))) return rc;
+        BPB_CUDA(h, cudaDeviceSynchronize());
+        BPB_CUDA(h, cudaMemcpy(h->obs_tab.ptr, h->obs_ptr.data(), h->obs_ptr.size() * 4, cudaMemcpyHostToDevice));
+        if (!h->obs_col.empty())
+            BPB_CUDA(h, cudaMemcpy((uint32_t *) h->obs_tab.ptr + h->obs_ptr.size(), h->obs_col.data(),
+                                   h->obs_col.size() * 4, cudaMemcpyHostToDevice));
+        h->obs_dirty = false;
+    }
+    const int mwp = round_up((g.m + 31) / 32, 4);
+    // rows per chunk: the unpacked decisions of a chunk stay on the device (n bytes per row), so bound those
+    const int64_t chunk_max = std::max<int64_t>(1024, std::min<int64_t>({batch, (int64_t) 1 << 18,
+                                                                         ((int64_t) 512 << 20) / std::max(g.n, 1)}));
+    const size_t cap = (size_t) chunk_max;
+    cudaError_t ce = cudaSuccess;
+#define B8_CUDA(call)                                                             \
+    if (rc == BPB_OK) {                                                           \
+        ce = (call);                                                              \
+        if (ce != cudaSuccess) {                                                  \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(ce);          \
+            rc = BPB_ERR_CUDA;                                                    \
+        }                                                                         \
+    }
+    if (with_osd) {
+        if ((rc = ensure(h, h->osd_count, 64, true, h->stream))) return rc;
+        B8_CUDA(cudaMemsetAsync((unsigned long long *) h->osd_count.ptr + 2, 0, 8, h->stream));
+    }
+    int64_t c = 0;
+    for (int64_t lo = 0; lo < batch && rc == BPB_OK; lo += chunk_max, ++c) {
+        const int s = (int) (c & 1);
+        const int64_t nb = std::min(chunk_max, batch - lo);
+        if ((rc = ensure(h, h->b8_in[s], cap * mb))) break;
+        if ((rc = ensure(h, h->b8_words[s], cap * mwp * 4))) break;
+        if ((rc = ensure(h, h->st_dec[s], cap * g.n))) break;
+        if ((rc = ensure(h, h->st_conv[s], cap))) break;
+        if ((rc = ensure(h, h->st_iters[s], cap * 4))) break;
+        if (decoding_b8 && (rc = ensure(h, h->b8_out[s], cap * nb8))) break;
+        if (observables_b8 && (rc = ensure(h, h->b8_obs[s], cap * std::max(kb, 1)))) break;
+        if (c >= 2) B8_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_k[s], 0));  // slot's input consumed
+        B8_CUDA(cudaMemcpyAsync(h->b8_in[s].ptr, syndromes_b8 + lo * mb, (size_t) nb * mb, cudaMemcpyHostToDevice, h->s_in));
+        B8_CUDA(cudaEventRecord(h->ev_in[s], h->s_in));
+        B8_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
+        if (c >= 2) B8_CUDA(cudaStreamWaitEvent(h->stream, h->ev_out[s], 0));  // slot's outputs drained
+        if (rc) break;
+        const int ugrid = (int) std::min<int64_t>((nb * mwp + 255) / 256, (int64_t) h->sm_count * 16);
+        unpack_b8_rows_kernel<<<ugrid, 256, 0, h->stream>>>((const uint8_t *) h->b8_in[s].ptr, nb, g.m, mb, mwp,
+                                                            (uint32_t *) h->b8_words[s].ptr);
+        B8_CUDA(cudaGetLastError());
+        h->launches += 1;
+        if (rc) break;
+        if (with_osd)
+            rc = enqueue_bposd_device(h, (const uint8_t *) h->b8_words[s].ptr, nb, (uint8_t *) h->st_dec[s].ptr,
+                                      (uint8_t *) h->st_conv[s].ptr, (int32_t *) h->st_iters[s].ptr, nullptr,
+                                      h->stream, kInputPacked);
+        else
+            rc = decode_device_core(h, kInputPacked, (const uint8_t *) h->b8_words[s].ptr, nb,
+                                    (uint8_t *) h->st_dec[s].ptr, (uint8_t *) h->st_conv[s].ptr,
+                                    (int32_t *) h->st_iters[s].ptr, nullptr, h->stream);
+        if (rc) break;
+        if (decoding_b8) {
+            const int pgrid = (int) std::min<int64_t>((nb * nb8 + 255) / 256, (int64_t) h->sm_count * 16);
+            pack_b8_rows_kernel<<<pgrid, 256, 0, h->stream>>>((const uint8_t *) h->st_dec[s].ptr, nb, g.n, nb8,
+                                                              (uint8_t *) h->b8_out[s].ptr);
+            B8_CUDA(cudaGetLastError());
+            h->launches += 1;
+        }
+        if (observables_b8) {
+            const int ogrid = (int) std::min<int64_t>((nb * kb + 255) / 256, (int64_t) h->sm_count * 16);
+            const uint32_t *optr = (const uint32_t *) h->obs_tab.ptr;
+            observables_b8_kernel<<<ogrid, 256, 0, h->stream>>>((const uint8_t *) h->st_dec[s].ptr, nb, g.n, h->obs_k, kb,
+                                                                optr, optr + h->obs_ptr.size(),
+                                                                (uint8_t *) h->b8_obs[s].ptr);
+            B8_CUDA(cudaGetLastError());
+            h->launches += 1;
+        }
+        B8_CUDA(cudaEventRecord(h->ev_k[s], h->stream));
+        B8_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_k[s], 0));
+        if (decoding_b8)
+            B8_CUDA(cudaMemcpyAsync(decoding_b8 + lo * nb8, h->b8_out[s].ptr, (size_t) nb * nb8, cudaMemcpyDeviceToHost, h->s_out));
+        if (observables_b8)
+            B8_CUDA(cudaMemcpyAsync(observables_b8 + lo * kb, h->b8_obs[s].ptr, (size_t) nb * kb, cudaMemcpyDeviceToHost, h->s_out));
+        if (converged)
+            B8_CUDA(cudaMemcpyAsync(converged + lo, h->st_conv[s].ptr, (size_t) nb, cudaMemcpyDeviceToHost, h->s_out));
+        if (iterations)
+            B8_CUDA(cudaMemcpyAsync(iterations + lo, h->st_iters[s].ptr, (size_t) nb * 4, cudaMemcpyDeviceToHost, h->s_out));
+        B8_CUDA(cudaEventRecord(h->ev_out[s], h->s_out));
+    }
+#undef B8_CUDA
+    // also on the error path: no copy into the caller's memory may be in flight when this returns
+    cudaStreamSynchronize(h->s_in);
+    const cudaError_t e1 = cudaStreamSynchronize(h->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(h->s_out);
+    if (rc == BPB_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        h->err = std::string("pipeline synchronise: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+        rc = BPB_ERR_CUDA;
+    }
+    h->have_last = false;
+    return rc;
 }
 
 int bpb_mc_bsc(bpb_decoder *h, uint64_t seed, int64_t first_run, int64_t runs, const double *flip_prob, int with_osd,

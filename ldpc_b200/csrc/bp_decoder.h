@@ -132,6 +132,11 @@ struct bpb_decoder {
     bpb::DeviceBuffer rel_order, rel_order_out, rel_msg;  // SERIAL_RELATIVE: configured / final schedule, scratch
     bool rel_order_valid = false;  // rel_order_out holds the schedule of a finished decode
     bool order_dirty = false;      // SERIAL_RELATIVE: only the configured schedule changed (cheap re-upload)
+    // bit-packed I/O (bpb_decode_batch_b8): staging per pipeline slot, observables matrix (CSR by observable)
+    bpb::DeviceBuffer b8_in[2], b8_words[2], b8_out[2], b8_obs[2], obs_tab;
+    int obs_k = 0;
+    std::vector<uint32_t> obs_ptr, obs_col;
+    bool obs_dirty = false;
     bpb::DeviceBuffer edge_msg;  // edge-parallel family: message scratch of the resident CTAs (large codes)
     bpb::DeviceBuffer mc_thresh, mc_err, mc_syn, mc_dec, mc_conv, mc_its, mc_counts;  // bpb_mc_bsc workspaces
     int osd_location = BPB_OSD_AUTO;  // where OSD-0 runs in the BP+OSD entry points

@@ -205,14 +205,26 @@ class SinterBpOsdDecoder:
                                   serial_schedule_order=self.serial_schedule_order, osd_method=self.osd_method,
                                   osd_order=self.osd_order, device=self.device)
         self._obs = sp.csr_matrix(matrices.observables_matrix, dtype=np.int32)
+        self.bposd.set_observables(self._obs)
 
     def decode_via_files(self, *, num_shots: int, num_dets: int, num_obs: int, dem_path, dets_b8_in_path,
                          obs_predictions_b8_out_path, tmp_dir=None) -> None:
         self.load_matrices(_matrices_from_dem_file(dem_path, num_dets, num_obs))
-        shots = read_b8(dets_b8_in_path, num_dets)
-        if shots.shape[0] != num_shots:
-            raise ValueError(f"expected {num_shots} shots, the file holds {shots.shape[0]}")
-        write_b8(obs_predictions_b8_out_path, self.decode_shots(shots))
+        # the b8 rows go to the device as they are: unpacking, BP + OSD-0, the observable parities and the packing of
+        # the predictions all happen there (bpb_decode_batch_b8); an all-zero shot decodes to the zero correction
+        nbytes = (num_dets + 7) // 8
+        raw = np.fromfile(str(dets_b8_in_path), dtype=np.uint8)
+        if nbytes == 0 or raw.size != num_shots * nbytes:
+            raise ValueError(f"expected {num_shots} shots of {nbytes} bytes, the file holds {raw.size} bytes")
+        if self.bposd.m != num_dets or self._obs.shape[0] != num_obs:
+            raise ValueError("the detector error model does not match num_dets / num_obs")
+        from ._capi import BpbError
+        try:
+            pred = self.bposd.decode_batch_b8(raw.reshape(num_shots, nbytes), decoding=False, observables=True)
+        except BpbError:
+            # codes the device OSD-0 kernel cannot hold (m > 1024 ...): unpacked route with the host elimination
+            pred = np.packbits(self.decode_shots(read_b8(dets_b8_in_path, num_dets)), axis=1, bitorder="little")
+        np.ascontiguousarray(pred).tofile(str(obs_predictions_b8_out_path))
 
     def decode_shots(self, shots: np.ndarray) -> np.ndarray:
         """``[shots, num_dets]`` detection events -> ``[shots, num_obs]`` predicted observable flips."""

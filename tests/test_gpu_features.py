@@ -245,3 +245,37 @@ def test_serial_relative_custom_order_and_decode_state(port_oracle):
         new = np.asarray(d.serial_schedule_order)
         assert sorted(new.tolist()) == list(range(240))
         cur = new
+
+
+@pytest.mark.parametrize("mk,p,osd", [(lambda: codes.regular_ldpc(1000, 3, 6, seed=1), 0.05, False),
+                                      (codes.bivariate_bicycle_144, 0.02, True),
+                                      (lambda: codes.rotated_surface_code_x(13), 0.05, True)],
+                         ids=["ldpc1000_bp", "bb144_bposd", "surface13_bposd"])
+def test_bit_packed_io_equals_unpacked(mk, p, osd):
+    """bpb_decode_batch_b8 (stim's b8 rows in, b8 decisions and observable parities out, everything in between on the
+    device) against decode_batch on the unpacked syndromes; m and n that are no multiples of 8 / 32 (surface code:
+    84 x 169) and garbage in the pad bits of the last input byte."""
+    H = mk()
+    m, n = H.shape
+    B = 5000
+    syn = codes.bsc_syndromes(H, p, B, seed=31)
+    kw = dict(max_iter=20, bp_method="ms", ms_scaling_factor=0.625)
+    cls = BpOsdDecoder if osd else BpDecoder
+    extra = dict(osd_method="osd0") if osd else dict(input_vector_type="syndrome")
+    d = cls(H, error_rate=p, **kw, **extra)
+    want = d.decode_batch(syn)
+    want_conv, want_its = d.converge_batch.copy(), d.iter_batch.copy()
+    packed = np.packbits(syn, axis=1, bitorder="little")
+    if m % 8:
+        packed[:, -1] |= np.uint8((0xff << (m % 8)) & 0xff)  # pad bits must be ignored
+    rng = np.random.default_rng(5)
+    O = (rng.random((11, n)) < 0.1).astype(np.uint8)
+    d.set_observables(O)
+    dec8, obs8 = d.decode_batch_b8(packed, decoding=True, observables=True)
+    got = np.unpackbits(dec8, axis=1, bitorder="little")[:, :n]
+    assert np.array_equal(got, want)
+    assert np.array_equal(d.converge_batch, want_conv) and np.array_equal(d.iter_batch, want_its)
+    want_obs = (want.astype(np.int32) @ O.T.astype(np.int32)) % 2
+    assert np.array_equal(np.unpackbits(obs8, axis=1, bitorder="little")[:, :11], want_obs.astype(np.uint8))
+    only_obs = d.decode_batch_b8(packed, decoding=False, observables=True)
+    assert np.array_equal(only_obs, obs8)
