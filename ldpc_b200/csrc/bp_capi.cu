@@ -435,6 +435,15 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     p.order_len = h->serial_entries;
     p.llr_last_only = h->llr_last_only ? 1 : 0;
     p.no_compaction = std::getenv("BPB_NO_COMPACTION") ? 1 : 0;
+    p.compact_num = 2;
+    p.compact_den = 1;
+    if (const char *ov = std::getenv("BPB_COMPACT_RATIO")) {  // tuning: "num/den"
+        int a = 0, b = 0;
+        if (std::sscanf(ov, "%d/%d", &a, &b) == 2 && a > 0 && b > 0) {
+            p.compact_num = a;
+            p.compact_den = b;
+        }
+    }
     p.serial_no_init = (h->serial_program_flags && h->uniform_prior && !std::getenv("BPB_SERIAL_INIT")) ? 1 : 0;
     BPB_CUDA(h, cudaEventRecord(h->kev0, st));
     k<<<grid, block, smem_bytes, st>>>(p);

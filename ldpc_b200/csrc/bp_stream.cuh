@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(256, (DC <= 8 && DV <= 4) ? ((SCHED == kParall
             uint32_t quads = live | (live >> 1) | (live >> 2) | (live >> 3);
             quads &= 0x11111111u;
             const int occupied = __popc(quads);
-            if (k > 0 && ((k + 3) >> 2) * 2 <= occupied) {
+            if (k > 0 && ((k + 3) >> 2) * p.compact_num <= occupied * p.compact_den) {
                 const bool was_live = idx >= 0;
                 const int src = (lane < k) ? (int) __fns(live, 0, lane + 1) : lane;  // old lane of new lane `lane`
                 const long long nidx = __shfl_sync(0xffffffffu, idx, src);

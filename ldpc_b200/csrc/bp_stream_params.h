@@ -35,6 +35,7 @@ struct StreamParams {
     uint32_t *handoff_list;             // their batch indices
     unsigned long long *iter_total;     // sum of iterations executed by this launch
     int serial_no_init;   // regular-code serial program carries the visited flags: no message initialisation in memory
+    int compact_num, compact_den;  // compact when sectors needed * num <= sectors occupied * den (default 2 / 1)
     int no_compaction;    // tuning / testing: keep live lanes where they are during the ramp-down
     int smem_graph, smem_syn;
     uint32_t smem_syn_off;  // word offset of the per-warp syndrome words in dynamic shared memory
