@@ -50,11 +50,11 @@ int ensure(bpb_decoder *h, bpb::DeviceBuffer &b, size_t bytes, bool zero = false
 }
 
 std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
-    return {&h->blob,     &h->order_d,   &h->counter_s[0], &h->counter_s[1],   &h->msg,        &h->dec_w,      &h->syn_w,    &h->llr_tile,
-            &h->packed_s[0], &h->packed_s[1],   &h->smem_tab,  &h->handoff,   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
+    return {&h->blob,     &h->order_d,   &h->counter_s[0], &h->counter_s[1],   &h->msg_s[0], &h->msg_s[1],        &h->dec_w_s[0], &h->dec_w_s[1],      &h->syn_w_s[0], &h->syn_w_s[1],    &h->llr_tile_s[0], &h->llr_tile_s[1],
+            &h->packed_s[0], &h->packed_s[1],   &h->smem_tab,  &h->handoff_s[0], &h->handoff_s[1],   &h->osd_llr,    &h->osd_fail_llr, &h->osd_fail_idx, &h->osd_count,  &h->st_in[0],  &h->st_in[1],   &h->st_dec[0],  &h->st_dec[1],
             &h->st_conv[0], &h->st_conv[1], &h->st_iters[0], &h->st_iters[1], &h->st_llr[0], &h->st_llr[1],
             &h->st_bp[0],   &h->st_bp[1],   &h->osd_conv,  &h->mc_thresh, &h->mc_err, &h->mc_syn, &h->mc_dec,
-            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg, &h->pair_tab, &h->rel_order, &h->rel_order_out, &h->rel_msg, &h->obs_tab,
+            &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg_s[0], &h->edge_msg_s[1], &h->pair_tab, &h->rel_order, &h->rel_order_out, &h->rel_msg, &h->obs_tab,
             &h->b8_in[0], &h->b8_in[1], &h->b8_words[0], &h->b8_words[1], &h->b8_out[0], &h->b8_out[1],
             &h->b8_obs[0], &h->b8_obs[1]};
 }
@@ -389,10 +389,10 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     const int grid = (int) grid64;
     const size_t warps = (size_t) grid * wpb;
     int rc;
-    if ((rc = ensure(h, h->msg, warps * (size_t) g.nnz * 32 * sizeof(double) * (generic ? 2 : 1)))) return rc;
-    if ((rc = ensure(h, h->dec_w, warps * (size_t) n_pad * 4, true, st))) return rc;
-    if ((rc = ensure(h, h->syn_w, p.smem_syn ? 16 : warps * (size_t) m_pad * 4, true, st))) return rc;
-    if (llr && (rc = ensure(h, h->llr_tile, warps * (size_t) g.n * 32 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->msg_s[h->slot], warps * (size_t) g.nnz * 32 * sizeof(double) * (generic ? 2 : 1)))) return rc;
+    if ((rc = ensure(h, h->dec_w_s[h->slot], warps * (size_t) n_pad * 4, true, st))) return rc;
+    if ((rc = ensure(h, h->syn_w_s[h->slot], p.smem_syn ? 16 : warps * (size_t) m_pad * 4, true, st))) return rc;
+    if (llr && (rc = ensure(h, h->llr_tile_s[h->slot], warps * (size_t) g.n * 32 * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->counter_s[h->slot], 64))) return rc;
     BPB_CUDA(h, cudaMemsetAsync(h->counter_s[h->slot].ptr, 0, 64, st));
     // second stage for the ramp-down (parallel schedule, when the thread-group kernels can take the code)
@@ -401,10 +401,10 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     const bool stage2_smem = h->smem_plan.ok && h->smem_plan.serial == (h->schedule == BPB_SERIAL);
     const bool stage2_edge = !stage2_smem && edge_able(h);
     const bool second_stage = (stage2_smem || stage2_edge) && h->max_iter > 16 && !std::getenv("BPB_NO_SECOND_STAGE");
-    if (second_stage && (rc = ensure(h, h->handoff, (size_t) warps * 32 * sizeof(uint32_t)))) return rc;
+    if (second_stage && (rc = ensure(h, h->handoff_s[h->slot], (size_t) warps * 32 * sizeof(uint32_t)))) return rc;
     p.iter_cap = second_stage ? 12 : h->max_iter + 1;
     p.handoff_count = (unsigned long long *) h->counter_s[h->slot].ptr + 1;
-    p.handoff_list = (uint32_t *) h->handoff.ptr;
+    p.handoff_list = (uint32_t *) h->handoff_s[h->slot].ptr;
     p.iter_total = (unsigned long long *) h->counter_s[h->slot].ptr + 3;
 
     p.blob = (const uint32_t *) h->blob.ptr;
@@ -423,10 +423,10 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     p.synd_packed = d_packed;
     p.batch = batch;
     p.counter = (unsigned long long *) h->counter_s[h->slot].ptr;
-    p.msg = (double *) h->msg.ptr;
-    p.dec_w = (uint32_t *) h->dec_w.ptr;
-    p.syn_w_g = (uint32_t *) h->syn_w.ptr;
-    p.llr_tile = (double *) h->llr_tile.ptr;
+    p.msg = (double *) h->msg_s[h->slot].ptr;
+    p.dec_w = (uint32_t *) h->dec_w_s[h->slot].ptr;
+    p.syn_w_g = (uint32_t *) h->syn_w_s[h->slot].ptr;
+    p.llr_tile = (double *) h->llr_tile_s[h->slot].ptr;
     p.out_dec = d_dec;
     p.out_conv = d_conv;
     p.out_iters = d_iters;
@@ -456,9 +456,9 @@ int launch_stream(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t bat
     h->last_block = block;
     if (second_stage) {
         rc = stage2_smem ? launch_smem(h, d_packed, mwp, batch, d_dec, d_conv, d_iters, d_llr, st,
-                                       (const uint32_t *) h->handoff.ptr, (const unsigned long long *) h->counter_s[h->slot].ptr + 1)
+                                       (const uint32_t *) h->handoff_s[h->slot].ptr, (const unsigned long long *) h->counter_s[h->slot].ptr + 1)
                          : launch_edge(h, d_packed, mwp, batch, d_dec, d_conv, d_iters, d_llr, st,
-                                       (const uint32_t *) h->handoff.ptr, (const unsigned long long *) h->counter_s[h->slot].ptr + 1);
+                                       (const uint32_t *) h->handoff_s[h->slot].ptr, (const unsigned long long *) h->counter_s[h->slot].ptr + 1);
         if (rc) return rc;
         h->last_family = BPB_KERNEL_STREAM;
         h->last_grid = grid;
@@ -742,7 +742,7 @@ int launch_edge(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     int rc;
     if ((rc = ensure(h, h->counter_s[h->slot], 64))) return rc;
     if (!index_list) BPB_CUDA(h, cudaMemsetAsync(h->counter_s[h->slot].ptr, 0, 64, st));
-    if (msg_global && (rc = ensure(h, h->edge_msg, (size_t) grid64 * msg_bytes))) return rc;
+    if (msg_global && (rc = ensure(h, h->edge_msg_s[h->slot], (size_t) grid64 * msg_bytes))) return rc;
     const uint32_t *blob = (const uint32_t *) h->blob.ptr;
     p.row_ptr = blob;
     p.col_idx = p.row_ptr + (g.m + 1);
@@ -763,7 +763,7 @@ int launch_edge(bpb_decoder *h, const uint32_t *d_packed, int mwp, int64_t batch
     p.counter = (unsigned long long *) h->counter_s[h->slot].ptr + 2;  // word 2: the second-stage / thread-group queue
     p.index_list = index_list;
     p.batch_dev = batch_dev;
-    p.msg_global = (double *) h->edge_msg.ptr;
+    p.msg_global = (double *) h->edge_msg_s[h->slot].ptr;
     p.out_dec = d_dec;
     p.out_conv = d_conv;
     p.out_iters = d_iters;
@@ -1348,13 +1348,12 @@ int host_pipeline(bpb_decoder *h, int input_type, const uint8_t *input, int64_t 
         if ((rc = ensure(h, h->osd_count, 64, true, h->stream))) return rc;
         PIPE_CUDA(cudaMemsetAsync((unsigned long long *) h->osd_count.ptr + 2, 0, 8, h->stream));
     }
-    // On-chip families keep no per-syndrome state in global memory, so the kernels of consecutive chunks may run
-    // concurrently: two compute streams (one per staging slot, each with its own work-queue counters and packed
-    // syndromes).  The CTAs of chunk c+1 start on the SMs that chunk c's CTAs leave, which hides the ramp-down of every
-    // chunk (the last syndromes of a chunk include 50-iteration non-convergers that would keep a few SMs busy and the
-    // rest idle for ~0.2 ms).  The streaming family shares its message tiles between launches and BP+OSD its failure
-    // lists: they stay on one stream.
-    const bool dual = smem_able && !with_osd && h->schedule == BPB_PARALLEL && h->kernel_pref != BPB_KERNEL_EDGE &&
+    // The kernels of consecutive chunks may run concurrently: two compute streams, one per staging slot, each with its
+    // own work-queue counters, packed syndromes and (streaming family) message tiles.  The CTAs of chunk c+1 start on
+    // the SMs that chunk c's CTAs leave, which hides the ramp-down of every chunk: 50-iteration non-convergers that keep
+    // a few SMs busy for ~0.2 ms in the on-chip families, the half-empty warps of the last iterations in the streaming
+    // family.  BP+OSD shares its failure lists between chunks and stays on one stream.
+    const bool dual = !with_osd && h->schedule != BPB_SERIAL_RELATIVE && h->kernel_pref != BPB_KERNEL_EDGE &&
                       batch > (int64_t) h->sm_count * 2 && !std::getenv("BPB_NO_DUAL_STREAM");
     if (dual && h->have_last) {
         PIPE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_last, 0));

@@ -120,10 +120,13 @@ struct bpb_decoder {
     int kernel_pref = BPB_KERNEL_AUTO;
     // device state
     bool graph_dirty = true;  // blob must be (re)uploaded (prior or order changed)
-    bpb::DeviceBuffer blob, order_d, msg, dec_w, syn_w, llr_tile, smem_tab, handoff;
+    bpb::DeviceBuffer blob, order_d, smem_tab;
     // work-queue counters and bit-packed syndromes: one set per pipeline slot, so that the kernels of consecutive
     // chunks of the host pipeline may overlap (on-chip families); everything else uses slot 0
     bpb::DeviceBuffer counter_s[2], packed_s[2];
+    // streaming family: message tiles, ballot words, LLR tiles, hand-off list (and the edge-parallel second stage's
+    // L2 scratch) -- also per slot, so that chunk c+1 ramps up on the SMs chunk c's ramp-down leaves
+    bpb::DeviceBuffer msg_s[2], dec_w_s[2], syn_w_s[2], llr_tile_s[2], handoff_s[2], edge_msg_s[2];
     int slot = 0;
     bool pipeline_dual = false;  // host_pipeline is alternating two compute streams
     cudaStream_t stream2 = nullptr;
@@ -137,7 +140,6 @@ struct bpb_decoder {
     int obs_k = 0;
     std::vector<uint32_t> obs_ptr, obs_col;
     bool obs_dirty = false;
-    bpb::DeviceBuffer edge_msg;  // edge-parallel family: message scratch of the resident CTAs (large codes)
     bpb::DeviceBuffer mc_thresh, mc_err, mc_syn, mc_dec, mc_conv, mc_its, mc_counts;  // bpb_mc_bsc workspaces
     int osd_location = BPB_OSD_AUTO;  // where OSD-0 runs in the BP+OSD entry points
     bool llr_last_only = false;       // BP+OSD: posterior LLRs are only needed for syndromes that ran max_iter
