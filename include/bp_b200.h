@@ -136,7 +136,7 @@ int bpb_mc_bsc(bpb_decoder *h, uint64_t seed, int64_t first_run, int64_t runs, c
  * stim's b8 layout, which is what sinter hands to SinterBpOsdDecoder.decode_via_files
  * (sinter_decoders/sinter_bposd_decoder.py:57-126): a row is ceil(bits / 8) bytes, bit k of the row is bit k % 8 of
  * byte k / 8.  The reference unpacks every shot to a uint8 vector, decodes it, multiplies the correction by the
- * observables matrix on the host and packs the result (:104-126).  Here the packed rows cross PCIe as they are
+ * observables matrix on the host and packs the result (:114-130).  Here the packed rows cross PCIe as they are
  * (ceil(m/8) bytes in, ceil(n/8) and / or ceil(k/8) bytes out per shot instead of m + n), unpacking, BP (+ OSD-0 on the
  * device when with_osd != 0), packing and the observable parities  obs = O x mod 2  all run on the device.
  * bpb_set_observables: O is k x n, given as nonzero coordinates.  decoding_b8 / observables_b8 / converged / iterations

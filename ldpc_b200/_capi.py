@@ -143,7 +143,8 @@ _POOL = {}            # bucket bytes (power of two) -> [ptr, ...] free pinned bl
 _POOL_BYTES = [0]     # bytes currently allocated through the pool (free + in use)
 _POOL_FREE = [0]      # bytes sitting free in the pool
 _POOL_LIMIT = int(os.environ.get("LDPC_B200_PINNED_LIMIT", str(8 << 30)))   # allocated through the pool at most
-_POOL_CACHE = int(os.environ.get("LDPC_B200_PINNED_CACHE", str(4 << 30)))   # kept free for reuse at most
+_POOL_CACHE = int(os.environ.get("LDPC_B200_PINNED_CACHE", str(8 << 30)))   # kept free for reuse at most (pinning
+# 5 GB takes about a second: a result buffer of the n = 10^4 workload must survive between calls)
 _POOL_LOCK = threading.Lock()  # MultiGpuBpDecoder / user threads call decode_batch concurrently
 
 

@@ -153,7 +153,7 @@ class BpDecoderBase:
     def set_observables(self, observables_matrix) -> None:
         """``k x n`` binary matrix O: ``decode_batch_b8(..., observables=True)`` then returns ``O x mod 2`` for every
         decoded row, computed on the device (the reference's sinter driver does this product per shot on the host,
-        sinter_bposd_decoder.py:121-124)."""
+        sinter_bposd_decoder.py:128-130)."""
         import scipy.sparse as sp
         O = sp.coo_matrix(observables_matrix)
         if O.shape[1] != self.n:

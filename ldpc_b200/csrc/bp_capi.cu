@@ -156,7 +156,7 @@ __global__ void pack_b8_rows_kernel(const uint8_t *__restrict__ dec, long long b
 }
 
 // predicted observable flips: obs = O x mod 2 for every row x of the decisions (what the reference's sinter driver
-// computes per shot on the host, sinter_bposd_decoder.py:121-124), b8 rows [B][ceil(k/8)]
+// computes per shot on the host, sinter_bposd_decoder.py:128-130), b8 rows [B][ceil(k/8)]
 __global__ void observables_b8_kernel(const uint8_t *__restrict__ dec, long long batch, int n, int k, int kb,
                                       const uint32_t *__restrict__ obs_ptr, const uint32_t *__restrict__ obs_col,
                                       uint8_t *__restrict__ out) {
