@@ -1353,7 +1353,9 @@ int host_pipeline(bpb_decoder *h, int input_type, const uint8_t *input, int64_t 
     // the SMs that chunk c's CTAs leave, which hides the ramp-down of every chunk: 50-iteration non-convergers that keep
     // a few SMs busy for ~0.2 ms in the on-chip families, the half-empty warps of the last iterations in the streaming
     // family.  BP+OSD shares its failure lists between chunks and stays on one stream.
-    const bool dual = !with_osd && h->schedule != BPB_SERIAL_RELATIVE && h->kernel_pref != BPB_KERNEL_EDGE &&
+    // (streaming family: a second set of message tiles only when one set is modest, 2368 warps x E x 256 bytes)
+    const bool tiles_ok = smem_able || (double) g.nnz * 256.0 * 16.0 * (double) h->sm_count < 40e9;
+    const bool dual = !with_osd && h->schedule != BPB_SERIAL_RELATIVE && h->kernel_pref != BPB_KERNEL_EDGE && tiles_ok &&
                       batch > (int64_t) h->sm_count * 2 && !std::getenv("BPB_NO_DUAL_STREAM");
     if (dual && h->have_last) {
         PIPE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_last, 0));
@@ -1881,6 +1883,10 @@ int bpb_set_devices(bpb_decoder *h, const int *ids, int count) {
             c->serial_order = h->serial_order;
             c->kernel_pref = h->kernel_pref;
             c->osd_location = h->osd_location;
+            c->obs_k = h->obs_k;
+            c->obs_ptr = h->obs_ptr;
+            c->obs_col = h->obs_col;
+            c->obs_dirty = h->obs_k > 0;
             c->graph_dirty = true;
             h->children.push_back(c);
         } else {

@@ -315,6 +315,12 @@ def test_shared_memory_placement_is_conflict_free(mk):
     assert inf.smem_family_available == 1
     assert inf.smem_bank_multiplicity == 1
     assert inf.smem_bytes_per_syndrome >= 8 * H.nnz
+    # the paired family places double2 slots by an 8-colouring over quarter-warps (16-byte accesses); hamming_code(5)
+    # (row degree 16 with column degree 5) is beyond its degree buckets
+    dc, dv = int(np.diff(H.tocsr().indptr).max()), int(np.diff(H.tocsc().indptr).max())
+    if not (dc > 8 and dv > 4):
+        assert inf.pair_family_available == 1
+        assert inf.pair_bank_multiplicity == 1
 
 
 def test_monte_carlo_driver_matches_reference_loop(port_oracle):
