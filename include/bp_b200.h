@@ -145,6 +145,16 @@ int bpb_set_observables(bpb_decoder *h, int k, int64_t nnz, const int32_t *rows,
 int bpb_decode_batch_b8(bpb_decoder *h, int with_osd, const uint8_t *syndromes_b8, int64_t batch, uint8_t *decoding_b8,
                         uint8_t *observables_b8, uint8_t *converged, int32_t *iterations);
 
+/* --- soft-information decoding (new) -----------------------------------------------
+ * Replaces BpDecoder::soft_info_decode_serial(soft_syndrome, cutoff, sigma) (bp.hpp:547-665), which the reference's
+ * SoftInfoBpDecoder.decode calls once per soft syndrome (_bp_decoder.pyx:761-785): serial-schedule min-sum (in the
+ * configured serial_schedule_order, ms_scaling_factor as set, maximum_iterations as set) where checks whose soft
+ * magnitude 2 s_i / sigma^2 is below `cutoff` take part as virtual variable nodes.  soft_syndromes is [B][m] doubles;
+ * llr ([B][n]) and soft_out ([B][m], the reference's soft_syndrome member after the decode) may be NULL. */
+int bpb_soft_info_decode_batch(bpb_decoder *h, const double *soft_syndromes, int64_t batch, double cutoff, double sigma,
+                               uint8_t *decoding, uint8_t *converged, int32_t *iterations, double *llr,
+                               double *soft_out);
+
 /* --- introspection ----------------------------------------------------------------------------- */
 typedef struct {
     int m, n;

@@ -60,6 +60,8 @@ cdef extern from "bp_b200.h":
     int bpb_set_osd_location(bpb_decoder *h, int v) nogil
     int bpb_set_devices(bpb_decoder *h, const int *ids, int count) nogil
     int bpb_get_last_schedule_order(bpb_decoder *h, int32_t *out, int len) nogil
+    int bpb_soft_info_decode_batch(bpb_decoder *h, const double *soft, int64_t batch, double cutoff, double sigma,
+                                   uint8_t *dec, uint8_t *conv, int32_t *its, double *llr, double *soft_out) nogil
     int bpb_set_observables(bpb_decoder *h, int k, int64_t nnz, const int32_t *rows, const int32_t *cols) nogil
     int bpb_decode_batch_b8(bpb_decoder *h, int with_osd, const uint8_t *syn, int64_t batch, uint8_t *dec,
                             uint8_t *obs, uint8_t *conv, int32_t *its) nogil
@@ -159,6 +161,18 @@ cdef class NativeHandle:
         cdef int32_t *pi = &its[0] if its is not None else NULL
         with nogil:
             rc = bpb_decode_batch_b8(self.h, with_osd, &syn[0, 0], B, pd, po, pc, pi)
+        self._check(rc)
+
+    def soft_info_decode_batch(self, const double[:, ::1] soft, double cutoff, double sigma, uint8_t[:, ::1] dec,
+                               uint8_t[::1] conv, int32_t[::1] its, double[:, ::1] llr, double[:, ::1] soft_out):
+        cdef int rc
+        cdef int64_t B = soft.shape[0]
+        if B == 0:
+            return
+        cdef double *pl = &llr[0, 0] if llr is not None else NULL
+        cdef double *ps = &soft_out[0, 0] if soft_out is not None else NULL
+        with nogil:
+            rc = bpb_soft_info_decode_batch(self.h, &soft[0, 0], B, cutoff, sigma, &dec[0, 0], &conv[0], &its[0], pl, ps)
         self._check(rc)
 
     def last_schedule_order(self, int32_t[::1] out):

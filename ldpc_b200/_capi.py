@@ -45,7 +45,7 @@ EXPORTS = [
     "bpb_decode_batch", "bpb_decode_batch_device", "bpb_osd0_host", "bpb_bposd_decode_batch", "bpb_get_info", "bpb_host_alloc",
     "bpb_host_free", "bpb_version", "bpb_set_osd_location", "bpb_set_devices", "bpb_bposd_decode_batch_device",
     "bpb_mc_bsc", "bpb_get_last_schedule_order", "bpb_libm_selfcheck",
-    "bpb_set_observables", "bpb_decode_batch_b8",
+    "bpb_set_observables", "bpb_decode_batch_b8", "bpb_soft_info_decode_batch",
 ]
 
 _lib = None
@@ -102,6 +102,8 @@ def lib():
     L.bpb_set_observables.argtypes = [vp, C.c_int, C.c_int64, _i32p, _i32p]
     L.bpb_decode_batch_b8.restype = C.c_int
     L.bpb_decode_batch_b8.argtypes = [vp, C.c_int, vp, C.c_int64, vp, vp, vp, vp]
+    L.bpb_soft_info_decode_batch.restype = C.c_int
+    L.bpb_soft_info_decode_batch.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_double, vp, vp, vp, vp, vp]
     L.bpb_libm_selfcheck.restype = C.c_int
     L.bpb_libm_selfcheck.argtypes = [C.c_int]
     L.bpb_get_last_schedule_order.restype = C.c_int

@@ -115,6 +115,15 @@ class Handle:
                                              _capi.host_ptr(its))
         _capi.check(self._ct, rc)
 
+    def soft_info_decode_batch(self, soft, cutoff, sigma, dec, conv, its, llr, soft_out):
+        if self._nh is not None:
+            return self._wrap(self._nh.soft_info_decode_batch, soft, float(cutoff), float(sigma), dec, conv, its, llr,
+                              soft_out)
+        rc = _capi.lib().bpb_soft_info_decode_batch(self._ct, _capi.host_ptr(soft), soft.shape[0], float(cutoff),
+                                                    float(sigma), _capi.host_ptr(dec), _capi.host_ptr(conv),
+                                                    _capi.host_ptr(its), _capi.host_ptr(llr), _capi.host_ptr(soft_out))
+        _capi.check(self._ct, rc)
+
     def last_schedule_order(self, n):
         """SERIAL_RELATIVE: the schedule the last syndrome of the last decode call ended with."""
         out = np.empty(n, dtype=np.int32)

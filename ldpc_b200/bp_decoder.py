@@ -491,3 +491,72 @@ class BpDecoder(BpDecoderBase):
     @property
     def decoding(self) -> np.ndarray:
         return self._decoding.astype(int)
+
+
+class SoftInfoBpDecoder(BpDecoderBase):
+    """Soft-information belief propagation (reference ``SoftInfoBpDecoder``, _bp_decoder.pyx:712-812, on top of
+    ``BpDecoder::soft_info_decode_serial``, src_cpp/bp.hpp:547-665): serial-schedule min-sum on a real-valued
+    syndrome; checks whose soft magnitude ``2 s_i / sigma^2`` is below ``cutoff`` take part as virtual variable nodes.
+    Same constructor as the reference (``cutoff``, ``sigma`` on top of the base keywords; schedule, method and input
+    type are forced to serial / minimum_sum / syndrome, :751-753).  ``decode(soft_syndrome)`` as in the reference;
+    ``decode_batch(soft_syndromes [B, m])`` decodes a batch in one GPU call."""
+
+    def __init__(self, pcm, error_rate: Optional[float] = None, error_channel: Optional[List[float]] = None,
+                 max_iter: Optional[int] = 0, bp_method: Optional[str] = "minimum_sum",
+                 ms_scaling_factor: Optional[float] = 1.0, cutoff: Optional[float] = np.inf, sigma: float = 2.0,
+                 **kwargs):
+        super().__init__(pcm, error_rate=error_rate, error_channel=error_channel, max_iter=max_iter,
+                         bp_method=bp_method, ms_scaling_factor=ms_scaling_factor, **kwargs)
+        self.cutoff = cutoff
+        if not isinstance(sigma, float) or sigma <= 0:
+            raise ValueError("The sigma value must be a float greater than 0.")
+        self.sigma = sigma
+        self.schedule = "serial"
+        self.bp_method = "minimum_sum"
+        self.input_vector_type = "syndrome"
+        self._soft_syndrome = np.zeros(self.m)
+        self.soft_syndrome_batch = None
+
+    def _soft_batch(self, soft: np.ndarray, want_llr: bool):
+        self._ensure_handle()
+        B = soft.shape[0]
+        dec = np.empty((B, self.n), dtype=np.uint8)
+        conv = np.empty((B,), dtype=np.uint8)
+        its = np.empty((B,), dtype=np.int32)
+        llr = np.empty((B, self.n), dtype=np.float64) if want_llr else None
+        out = np.empty((B, self.m), dtype=np.float64)
+        self._native.soft_info_decode_batch(soft, self.cutoff, self.sigma, dec, conv, its, llr, out)
+        return dec, conv.astype(bool), its, llr, out
+
+    def decode(self, soft_info_syndrome: np.ndarray) -> np.ndarray:
+        soft = np.ascontiguousarray(np.asarray(soft_info_syndrome, dtype=np.float64).reshape(1, -1))
+        if soft.shape[1] != self.m:
+            raise ValueError(f"The soft syndrome must have length {self.m}. Not {soft.shape[1]}.")
+        dec, conv, its, llr, out = self._soft_batch(soft, True)
+        self._decoding = dec[0]
+        self._converge = bool(conv[0])
+        self._iterations = int(its[0])
+        self._log_prob_ratios = llr[0]
+        self._soft_syndrome = out[0]
+        return dec[0].copy()
+
+    def decode_batch(self, soft_info_syndromes: np.ndarray, return_llr: bool = False) -> np.ndarray:
+        soft = np.ascontiguousarray(np.asarray(soft_info_syndromes, dtype=np.float64))
+        if soft.ndim != 2 or soft.shape[1] != self.m:
+            raise ValueError(f"The soft syndromes must have shape [batch, {self.m}].")
+        if soft.shape[0] == 0:
+            self.converge_batch, self.iter_batch = np.zeros(0, bool), np.zeros(0, np.int32)
+            return np.zeros((0, self.n), np.uint8)
+        dec, conv, its, llr, out = self._soft_batch(soft, return_llr)
+        self.converge_batch, self.iter_batch, self.log_prob_ratios_batch = conv, its, llr
+        self.soft_syndrome_batch = out
+        return dec
+
+    @property
+    def soft_syndrome(self) -> np.ndarray:
+        return np.asarray(self._soft_syndrome, dtype=float).copy()
+
+    @property
+    def decoding(self) -> np.ndarray:
+        return np.asarray(self._decoding).astype(int)
+

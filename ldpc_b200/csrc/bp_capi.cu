@@ -56,7 +56,7 @@ std::vector<bpb::DeviceBuffer *> all_buffers(bpb_decoder *h) {
             &h->st_bp[0],   &h->st_bp[1],   &h->osd_conv,  &h->mc_thresh, &h->mc_err, &h->mc_syn, &h->mc_dec,
             &h->mc_conv,    &h->mc_its,     &h->mc_counts, &h->edge_msg_s[0], &h->edge_msg_s[1], &h->pair_tab, &h->rel_order, &h->rel_order_out, &h->rel_msg, &h->obs_tab,
             &h->b8_in[0], &h->b8_in[1], &h->b8_words[0], &h->b8_words[1], &h->b8_out[0], &h->b8_out[1],
-            &h->b8_obs[0], &h->b8_obs[1]};
+            &h->b8_obs[0], &h->b8_obs[1], &h->soft_in, &h->soft_out, &h->soft_llr};
 }
 
 void release(bpb::DeviceBuffer &b) {
@@ -1751,6 +1751,83 @@ int bpb_decode_batch_b8(bpb_decoder *h, int with_osd, const uint8_t *syndromes_b
     }
     h->have_last = false;
     return rc;
+}
+
+int bpb_soft_info_decode_batch(bpb_decoder *h, const double *soft_syndromes, int64_t batch, double cutoff, double sigma,
+                               uint8_t *decoding, uint8_t *converged, int32_t *iterations, double *llr,
+                               double *soft_out) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (batch < 0 || (batch > 0 && (!soft_syndromes || !decoding))) {
+        h->err = "bad decode arguments";
+        return BPB_ERR_ARG;
+    }
+    if (!(sigma > 0)) {
+        h->err = "The sigma value must be a float greater than 0.";  // _bp_decoder.pyx:748-749
+        return BPB_ERR_ARG;
+    }
+    if (!h->children.empty()) {
+        h->err = "bpb_soft_info_decode_batch is not split over devices; use a single-device handle";
+        return BPB_ERR_UNSUPPORTED;
+    }
+    if (batch == 0) return BPB_OK;
+    BPB_CUDA(h, cudaSetDevice(h->device));
+    if (h->graph_dirty && (rc = upload_graph(h))) return rc;
+    const bpb::HostGraph &g = h->g;
+    cudaStream_t st = h->stream;
+    if (h->order_dirty) {
+        BPB_CUDA(h, cudaStreamSynchronize(st));
+        BPB_CUDA(h, cudaMemcpy(h->rel_order.ptr, h->serial_order.data(), h->serial_order.size() * sizeof(uint32_t),
+                               cudaMemcpyHostToDevice));
+        h->order_dirty = false;
+    }
+    const size_t row_bytes = (size_t) g.m * 16 + (size_t) g.n * 9 + 5;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t) 1 << 30) / (int64_t) row_bytes));
+    const size_t cap = (size_t) chunk;
+    if ((rc = ensure(h, h->soft_in, cap * g.m * 8))) return rc;
+    if (soft_out && (rc = ensure(h, h->soft_out, cap * g.m * 8))) return rc;
+    if (llr && (rc = ensure(h, h->soft_llr, cap * g.n * 8))) return rc;
+    if ((rc = ensure(h, h->st_dec[0], cap * g.n))) return rc;
+    if ((rc = ensure(h, h->st_conv[0], cap))) return rc;
+    if ((rc = ensure(h, h->st_iters[0], cap * 4))) return rc;
+    if ((rc = ensure(h, h->counter_s[0], 64))) return rc;
+    for (int64_t lo = 0; lo < batch; lo += chunk) {
+        const int64_t nb = std::min(chunk, batch - lo);
+        BPB_CUDA(h, cudaMemcpyAsync(h->soft_in.ptr, soft_syndromes + lo * g.m, (size_t) nb * g.m * 8,
+                                    cudaMemcpyHostToDevice, st));
+        BPB_CUDA(h, cudaMemsetAsync(h->counter_s[0].ptr, 0, 64, st));
+        const int e = bpb::launch_softinfo_kernel(g, h->sm_count, h->max_smem_optin, (const uint32_t *) h->blob.ptr,
+                                                  h->prior_off, h->max_iter, h->ms_scaling, cutoff, sigma,
+                                                  (const uint32_t *) h->rel_order.ptr, (int) h->serial_order.size(),
+                                                  (const double *) h->soft_in.ptr, nb,
+                                                  (unsigned long long *) h->counter_s[0].ptr + 2, &h->rel_msg,
+                                                  (uint8_t *) h->st_dec[0].ptr, (uint8_t *) h->st_conv[0].ptr,
+                                                  (int32_t *) h->st_iters[0].ptr,
+                                                  llr ? (double *) h->soft_llr.ptr : nullptr,
+                                                  soft_out ? (double *) h->soft_out.ptr : nullptr, st);
+        if (e == -1) {
+            h->err = "soft-information decoding: the code does not fit the kernel (column degree > 32 or n, m beyond shared memory)";
+            return BPB_ERR_UNSUPPORTED;
+        }
+        if (e) {
+            h->err = std::string("bp_softinfo_kernel launch: ") + cudaGetErrorString((cudaError_t) e);
+            return BPB_ERR_CUDA;
+        }
+        h->launches += 1;
+        h->last_family = BPB_KERNEL_EDGE;
+        BPB_CUDA(h, cudaMemcpyAsync(decoding + lo * g.n, h->st_dec[0].ptr, (size_t) nb * g.n, cudaMemcpyDeviceToHost, st));
+        if (converged)
+            BPB_CUDA(h, cudaMemcpyAsync(converged + lo, h->st_conv[0].ptr, (size_t) nb, cudaMemcpyDeviceToHost, st));
+        if (iterations)
+            BPB_CUDA(h, cudaMemcpyAsync(iterations + lo, h->st_iters[0].ptr, (size_t) nb * 4, cudaMemcpyDeviceToHost, st));
+        if (llr)
+            BPB_CUDA(h, cudaMemcpyAsync(llr + lo * g.n, h->soft_llr.ptr, (size_t) nb * g.n * 8, cudaMemcpyDeviceToHost, st));
+        if (soft_out)
+            BPB_CUDA(h, cudaMemcpyAsync(soft_out + lo * g.m, h->soft_out.ptr, (size_t) nb * g.m * 8, cudaMemcpyDeviceToHost, st));
+        BPB_CUDA(h, cudaStreamSynchronize(st));
+    }
+    h->have_last = false;
+    return BPB_OK;
 }
 
 int bpb_mc_bsc(bpb_decoder *h, uint64_t seed, int64_t first_run, int64_t runs, const double *flip_prob, int with_osd,

@@ -79,6 +79,13 @@ int launch_relative_kernel(const HostGraph &g, int sm_count, int max_smem_optin,
                            int32_t *d_iters, double *d_llr, int llr_last_only, int32_t *d_order_out, cudaStream_t st,
                            int *grid_out);
 
+// soft-information serial min-sum (bp_relative.cu): one warp per soft syndrome; cudaError_t value, -1 = does not fit
+int launch_softinfo_kernel(const HostGraph &g, int sm_count, int max_smem_optin, const uint32_t *d_blob,
+                           uint32_t prior_off, int max_iter, double ms_scaling, double cutoff, double sigma,
+                           const uint32_t *d_order0, int order_len, const double *d_soft, int64_t batch,
+                           unsigned long long *d_counter, DeviceBuffer *scratch, uint8_t *d_dec, uint8_t *d_conv,
+                           int32_t *d_iters, double *d_llr, double *d_soft_out, cudaStream_t st);
+
 // On-device BSC sampling and scoring (mc_device.cu)
 int launch_mc_generate(const uint32_t *d_row_ptr, const uint32_t *d_col_idx, const unsigned long long *d_thresh, int m,
                        int n, int nw, int mwp, unsigned long long seed, unsigned long long first_run, int64_t batch,
@@ -132,6 +139,7 @@ struct bpb_decoder {
     cudaStream_t stream2 = nullptr;
     bpb::DeviceBuffer osd_llr, osd_fail_llr, osd_fail_idx, osd_count;  // BP+OSD batch path
     bpb::OsdDevicePlan osd_plan;
+    bpb::DeviceBuffer soft_in, soft_out, soft_llr;  // bpb_soft_info_decode_batch staging
     bpb::DeviceBuffer rel_order, rel_order_out, rel_msg;  // SERIAL_RELATIVE: configured / final schedule, scratch
     bool rel_order_valid = false;  // rel_order_out holds the schedule of a finished decode
     bool order_dirty = false;      // SERIAL_RELATIVE: only the configured schedule changed (cheap re-upload)

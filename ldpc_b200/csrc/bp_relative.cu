@@ -164,6 +164,219 @@ __global__ void __launch_bounds__(32) bp_relative_kernel(const RelParams p) {
     }
 }
 
+// ---- soft-information serial min-sum (reference src_cpp/bp.hpp:547-665, SoftInfoBpDecoder) -------------------------
+// The syndrome arrives as real numbers: soft_i = 2 s_i / sigma^2, hard bit = (soft_i <= 0).  A check whose soft
+// magnitude is below `cutoff` and below the smallest incoming magnitude acts as a virtual variable node: it propagates
+// its own magnitude and is refreshed from the messages or flipped (:604-628), so every check carries mutable state
+// through the sweep.  Same mapping as the SERIAL_RELATIVE kernel: one warp per syndrome, bits in the configured
+// order, lane k takes the bit's k-th check (the checks of one bit are distinct, so the lanes touch distinct state).
+struct SoftParams {
+    const uint32_t *row_ptr, *col_idx, *col_ptr, *csc2csr, *row_idx;
+    const double *prior;
+    int m, n, nnz;
+    int max_iter;
+    double ms_scaling, cutoff, sigma;
+    const uint32_t *order0;
+    int order_len;
+    uint32_t off_soft, off_dec, off_syn, off_msg;  // byte offsets in dynamic shared memory (LLRs at 0)
+    const double *soft_in;  // [B][m]
+    long long batch;
+    unsigned long long *counter;
+    double *msg_global;
+    uint8_t *out_dec;
+    uint8_t *out_conv;
+    int32_t *out_iters;
+    double *out_llr;   // [B][n] or null
+    double *out_soft;  // [B][m] or null: the soft syndrome after decoding
+};
+
+template <bool MSG_GLOBAL>
+__global__ void __launch_bounds__(32) bp_softinfo_kernel(const SoftParams p) {
+    extern __shared__ __align__(16) uint8_t ssm[];
+    const int lane = threadIdx.x;
+    const int m = p.m, n = p.n, nnz = p.nnz;
+    double *llr = reinterpret_cast<double *>(ssm);
+    double *soft = reinterpret_cast<double *>(ssm + p.off_soft);
+    uint8_t *dec = ssm + p.off_dec;
+    uint8_t *syn = ssm + p.off_syn;
+    double *msg = MSG_GLOBAL ? (p.msg_global + (size_t) blockIdx.x * (size_t) nnz)
+                             : reinterpret_cast<double *>(ssm + p.off_msg);
+    __shared__ long long ctl;
+    for (;;) {
+        if (lane == 0) {
+            const long long claim = (long long) atomicAdd(p.counter, 1ull);
+            ctl = claim < p.batch ? claim : -1;
+        }
+        __syncwarp();
+        const long long idx = ctl;
+        __syncwarp();
+        if (idx < 0) break;
+        const double *in = p.soft_in + idx * m;
+        for (int i = lane; i < m; i += 32) {  // bp.hpp:551-558
+            const double sv = 2 * in[i] / (p.sigma * p.sigma);
+            soft[i] = sv;
+            syn[i] = (sv <= 0) ? 1 : 0;
+        }
+        for (int j = lane; j < n; j += 32) {
+            llr[j] = p.prior[j];
+            dec[j] = 0;
+        }
+        for (int e = lane; e < nnz; e += 32) msg[e] = p.prior[p.col_idx[e]];  // bp.hpp:147-157
+        __syncwarp();
+        int it = 0;
+        bool conv = false;
+        while (it < p.max_iter && !conv) {  // a converged decode skips its remaining iterations (:571-573)
+            ++it;
+            for (int oi = 0; oi < p.order_len; ++oi) {
+                const int j = (int) p.order0[oi];
+                const uint32_t cb = p.col_ptr[j];
+                const int deg = (int) (p.col_ptr[j + 1] - cb);
+                double c = 0.0;
+                uint32_t e = 0;
+                if (lane < deg) {
+                    e = p.csc2csr[cb + lane];
+                    const uint32_t i = p.row_idx[cb + lane];
+                    const uint32_t rb = p.row_ptr[i], re = p.row_ptr[i + 1];
+                    uint32_t sgn = 0;
+                    double temp = DBL_MAX;
+                    for (uint32_t f = rb; f < re; ++f) {  // :590-600
+                        if (f == e) continue;
+                        const double b = msg[f];
+                        if (fabs(b) < temp) temp = fabs(b);
+                        if (b <= 0) sgn ^= 1u;
+                    }
+                    const double min_msg = temp;
+                    double propagated = min_msg;
+                    const double own = msg[e];
+                    uint32_t s = syn[i];
+                    const double mag = fabs(soft[i]);
+                    if (mag < p.cutoff && mag < fabs(min_msg)) {  // :604-628
+                        propagated = mag;
+                        const uint32_t check_sgn = sgn ^ ((own <= 0) ? 1u : 0u);
+                        if (check_sgn == s) {
+                            const double v = (fabs(own) < min_msg) ? fabs(own) : min_msg;
+                            soft[i] = (s ? -1.0 : 1.0) * v;
+                        } else {
+                            s ^= 1u;
+                            syn[i] = (uint8_t) s;
+                            soft[i] = soft[i] * -1;
+                        }
+                    }
+                    sgn ^= s;
+                    c = (p.ms_scaling * (sgn ? -1.0 : 1.0)) * propagated;  // :631
+                }
+                __syncwarp();
+                double t = p.prior[j], mypre = 0.0, mysuf = 0.0;
+                for (int k = 0; k < deg; ++k) {
+                    const double ck = __shfl_sync(0xffffffffu, c, k);
+                    if (lane == k) mypre = t;
+                    t += ck;
+                }
+                double u = 0.0;
+                for (int k = deg - 1; k >= 0; --k) {
+                    const double ck = __shfl_sync(0xffffffffu, c, k);
+                    if (lane == k) mysuf = u;
+                    u += ck;
+                }
+                if (lane < deg) msg[e] = mypre + mysuf;
+                if (lane == 0) {
+                    llr[j] = t;
+                    dec[j] = (t <= 0) ? 1 : 0;
+                }
+                __syncwarp();
+            }
+            bool bad = false;  // :646-660: H x against the (possibly flipped) hard syndrome
+            for (int i = lane; i < m; i += 32) {
+                uint32_t x = syn[i];
+                for (uint32_t f = p.row_ptr[i]; f < p.row_ptr[i + 1]; ++f) x ^= dec[p.col_idx[f]];
+                bad |= (x != 0);
+            }
+            conv = !__any_sync(0xffffffffu, bad);
+        }
+        uint8_t *drow = p.out_dec + idx * n;
+        for (int j = lane; j < n; j += 32) drow[j] = dec[j];
+        if (p.out_llr)
+            for (int j = lane; j < n; j += 32) p.out_llr[idx * n + j] = llr[j];
+        if (p.out_soft)
+            for (int i = lane; i < m; i += 32) p.out_soft[idx * m + i] = soft[i];
+        if (lane == 0) {
+            if (p.out_iters) p.out_iters[idx] = it;
+            if (p.out_conv) p.out_conv[idx] = conv ? 1 : 0;
+        }
+        __syncwarp();
+    }
+}
+
+int launch_softinfo_kernel(const HostGraph &g, int sm_count, int max_smem_optin, const uint32_t *d_blob,
+                           uint32_t prior_off, int max_iter, double ms_scaling, double cutoff, double sigma,
+                           const uint32_t *d_order0, int order_len, const double *d_soft, int64_t batch,
+                           unsigned long long *d_counter, DeviceBuffer *scratch, uint8_t *d_dec, uint8_t *d_conv,
+                           int32_t *d_iters, double *d_llr, double *d_soft_out, cudaStream_t st) {
+    if (g.max_col_degree > 32) return -1;
+    SoftParams p{};
+    p.row_ptr = d_blob;
+    p.col_idx = p.row_ptr + (g.m + 1);
+    p.col_ptr = p.col_idx + g.nnz;
+    p.csc2csr = p.col_ptr + (g.n + 1);
+    p.row_idx = p.csc2csr + g.nnz;
+    p.prior = reinterpret_cast<const double *>(d_blob + prior_off);
+    p.m = g.m;
+    p.n = g.n;
+    p.nnz = g.nnz;
+    p.max_iter = max_iter;
+    p.ms_scaling = ms_scaling;
+    p.cutoff = cutoff;
+    p.sigma = sigma;
+    p.order0 = d_order0;
+    p.order_len = order_len;
+    auto up = [](size_t x, size_t q) { return (x + q - 1) / q * q; };
+    size_t off = (size_t) g.n * 8;
+    p.off_soft = (uint32_t) off;
+    off += (size_t) g.m * 8;
+    p.off_dec = (uint32_t) off;
+    off += up((size_t) g.n, 8);
+    p.off_syn = (uint32_t) off;
+    off += up((size_t) g.m, 16);
+    p.off_msg = (uint32_t) off;
+    const size_t fixed = off;
+    if (fixed > (size_t) max_smem_optin) return -1;
+    const bool msg_global = fixed + (size_t) g.nnz * 8 > (size_t) max_smem_optin / 4;
+    const size_t smem = fixed + (msg_global ? 0 : (size_t) g.nnz * 8);
+    using K = void (*)(const SoftParams);
+    K k = msg_global ? (K) bp_softinfo_kernel<true> : (K) bp_softinfo_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 32, smem);
+    if (e != cudaSuccess) return (int) e;
+    if (occ < 1) return -1;
+    int64_t grid = std::min<int64_t>((int64_t) occ * sm_count, batch);
+    if (msg_global) {
+        grid = std::min<int64_t>(grid, std::max<int64_t>(1, ((int64_t) 100 << 20) / ((int64_t) g.nnz * 8)));
+        const size_t need = (size_t) grid * (size_t) g.nnz * 8;
+        if (scratch->bytes < need) {
+            if (scratch->ptr) cudaFree(scratch->ptr);
+            scratch->ptr = nullptr;
+            scratch->bytes = 0;
+            e = cudaMalloc(&scratch->ptr, need);
+            if (e != cudaSuccess) return (int) e;
+            scratch->bytes = need;
+        }
+        p.msg_global = (double *) scratch->ptr;
+    }
+    if (grid < 1) grid = 1;
+    p.soft_in = d_soft;
+    p.batch = batch;
+    p.counter = d_counter;
+    p.out_dec = d_dec;
+    p.out_conv = d_conv;
+    p.out_iters = d_iters;
+    p.out_llr = d_llr;
+    p.out_soft = d_soft_out;
+    k<<<(int) grid, 32, smem, st>>>(p);
+    return (int) cudaGetLastError();
+}
+
 // Host side.  Returns a cudaError_t value (0 = ok), -1 when the code does not fit this kernel.
 int launch_relative_kernel(const HostGraph &g, int sm_count, int max_smem_optin, const uint32_t *d_blob,
                            uint32_t prior_off, int method, int max_iter, double ms_scaling, const uint32_t *d_order0,

@@ -70,6 +70,14 @@ class PortOracle(_Lib):
         g = self.lib.bpo_osd0_batch
         g.restype = C.c_int
         g.argtypes = [C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _u8p, _f64p, C.c_int64, _u8p]
+        self.lib.bpo_soft_info_decode_batch.restype = C.c_int
+        self.lib.bpo_soft_info_decode_batch.argtypes = _SOFT_ARGS
+
+    def soft_info_decode_batch(self, H, soft, channel, max_iter, ms_scaling_factor=1.0, cutoff=np.inf, sigma=2.0,
+                               serial_schedule_order=None):
+        """Restatement of soft_info_decode_serial (bp.hpp:547-665) -> (decoding, converged, iters, llr, soft)."""
+        return _soft_call(self.lib.bpo_soft_info_decode_batch, H, soft, channel, max_iter, ms_scaling_factor, cutoff,
+                          sigma, serial_schedule_order)
 
     def decode_batch(self, H, syndromes, channel, max_iter, bp_method="ms", schedule="parallel",
                      ms_scaling_factor=1.0, serial_schedule_order=None, want_llr=True):
@@ -103,6 +111,30 @@ class PortOracle(_Lib):
         return out
 
 
+def _soft_call(fn, H, soft, channel, max_iter, ms_scaling_factor, cutoff, sigma, serial_schedule_order):
+    m, n, rows, cols = _coo(H)
+    sf = np.ascontiguousarray(soft, dtype=np.float64).reshape(-1, m)
+    B = sf.shape[0]
+    ch = np.ascontiguousarray(np.broadcast_to(np.asarray(channel, dtype=np.float64), (n,)))
+    order = None if serial_schedule_order is None else np.ascontiguousarray(serial_schedule_order, dtype=np.int32)
+    dec = np.zeros((B, n), np.uint8)
+    conv = np.zeros(B, np.uint8)
+    its = np.zeros(B, np.int32)
+    llr = np.zeros((B, n), np.float64)
+    out_soft = np.zeros((B, m), np.float64)
+    rc = fn(m, n, rows.size, _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(ch, _f64p), int(max_iter),
+            float(ms_scaling_factor), _ptr(order, _i32p), 0 if order is None else order.size, float(cutoff),
+            float(sigma), _ptr(sf, _f64p), B, _ptr(dec, _u8p), _ptr(conv, _u8p), _ptr(its, _i32p), _ptr(llr, _f64p),
+            _ptr(out_soft, _f64p))
+    if rc < 0:
+        raise RuntimeError("soft-info decode failed")
+    return dec, conv.astype(bool), its, llr, out_soft
+
+
+_SOFT_ARGS = [C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, C.c_int, C.c_double, _i32p, C.c_int, C.c_double,
+              C.c_double, _f64p, C.c_int64, _u8p, _u8p, _i32p, _f64p, _f64p]
+
+
 class RefOracle(_Lib):
     """The unmodified reference C++ (ldpc::bp::BpDecoder / ldpc::osd::OsdDecoder)."""
 
@@ -117,6 +149,15 @@ class RefOracle(_Lib):
         g.argtypes = [C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, C.c_int, C.c_int, C.c_int, C.c_double, _u8p,
                       C.c_int64, _u8p]
         self.lib.ref_hardware_threads.restype = C.c_int
+        if hasattr(self.lib, "ref_soft_info_decode_batch"):
+            self.lib.ref_soft_info_decode_batch.restype = C.c_double
+            self.lib.ref_soft_info_decode_batch.argtypes = _SOFT_ARGS
+
+    def soft_info_decode_batch(self, H, soft, channel, max_iter, ms_scaling_factor=1.0, cutoff=np.inf, sigma=2.0,
+                               serial_schedule_order=None):
+        """ldpc::bp::BpDecoder::soft_info_decode_serial per row -> (decoding, converged, iters, llr, soft_syndrome)."""
+        return _soft_call(self.lib.ref_soft_info_decode_batch, H, soft, channel, max_iter, ms_scaling_factor, cutoff,
+                          sigma, serial_schedule_order)
 
     def hardware_threads(self) -> int:
         return int(self.lib.ref_hardware_threads())

@@ -495,6 +495,111 @@ int bpo_decode_batch(int m, int n, int64_t nnz, const int32_t *rows, const int32
     return 0;
 }
 
+/*
+ * soft_info_decode_serial (bp.hpp:547-665): serial min-sum with a SOFT syndrome.  soft_syndrome_i = 2 s_i / sigma^2,
+ * hard syndrome bit = (soft_syndrome_i <= 0).  While a check's soft magnitude is below `cutoff` and below the minimum
+ * incoming magnitude, the check acts as a "virtual" variable: it propagates its own magnitude, and is either refreshed
+ * from the messages (when the parity of the incoming signs agrees with its hard bit) or flipped (:606-628).  The
+ * convergence test compares H x with the (possibly flipped) hard syndrome (:649-660); once converged the remaining
+ * iterations are skipped and `iterations` keeps the value of the converging sweep (:571-573,661).
+ * Decodes a batch, one soft syndrome after another, as B independent calls would.
+ */
+int bpo_soft_info_decode_batch(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *cols,
+                               const double *channel, int max_iter, double ms_scaling_factor,
+                               const int32_t *serial_order, int serial_order_len, double cutoff, double sigma,
+                               const double *soft_syndromes, int64_t batch, uint8_t *out_decoding,
+                               uint8_t *out_converged, int32_t *out_iters, double *out_llr, double *out_soft) {
+    bpo_graph g;
+    int rc = bpo_graph_build(&g, m, n, nnz, rows, cols);
+    if (rc) return rc;
+    size_t ne = (size_t) (g.nnz > 0 ? g.nnz : 1);
+    double *b2c = (double *) calloc(ne, sizeof(double)), *c2b = (double *) calloc(ne, sizeof(double));
+    double *llr = (double *) calloc((size_t) n + 1, sizeof(double));
+    double *soft = (double *) calloc((size_t) m + 1, sizeof(double));
+    uint8_t *syn = (uint8_t *) calloc((size_t) m + 1, 1), *dec = (uint8_t *) calloc((size_t) n + 1, 1);
+    for (int64_t b = 0; b < batch; b++) {
+        const double *in = soft_syndromes + b * (int64_t) m;
+        for (int i = 0; i < m; i++) { /* :551-558 */
+            soft[i] = 2 * in[i] / (sigma * sigma);
+            syn[i] = (soft[i] <= 0) ? 1 : 0;
+        }
+        for (int j = 0; j < n; j++) { /* initialise_log_domain_bp, bp.hpp:147-157 */
+            double pr = log((1 - channel[j]) / channel[j]);
+            for (int p = g.col_ptr[j]; p < g.col_ptr[j + 1]; p++) b2c[g.csc2csr[p]] = pr;
+        }
+        int converged = 0, iterations = 0;
+        for (int it = 1; it <= max_iter; it++) {
+            if (converged) continue; /* :571-573 */
+            for (int oi = 0; oi < (serial_order ? serial_order_len : n); oi++) {
+                int j = serial_order ? serial_order[oi] : oi;
+                llr[j] = log((1 - channel[j]) / channel[j]);
+                for (int p = g.col_ptr[j]; p < g.col_ptr[j + 1]; p++) {
+                    int e = g.csc2csr[p], i = g.row_idx[p];
+                    int sgn = 0;
+                    double temp = DBL_MAX;
+                    for (int f = g.row_ptr[i]; f < g.row_ptr[i + 1]; f++) {
+                        if (f == e) continue;
+                        if (fabs(b2c[f]) < temp) temp = fabs(b2c[f]);
+                        if (b2c[f] <= 0) sgn ^= 1;
+                    }
+                    double min_msg = temp, propagated = min_msg;
+                    double mag = fabs(soft[i]);
+                    if (mag < cutoff) { /* :604-628 */
+                        if (mag < fabs(min_msg)) {
+                            propagated = mag;
+                            int check_sgn = sgn;
+                            if (b2c[e] <= 0) check_sgn ^= 1;
+                            if (check_sgn == syn[i]) {
+                                if (fabs(b2c[e]) < min_msg)
+                                    soft[i] = pow(-1, syn[i]) * fabs(b2c[e]);
+                                else
+                                    soft[i] = pow(-1, syn[i]) * min_msg;
+                            } else {
+                                syn[i] ^= 1;
+                                soft[i] *= -1;
+                            }
+                        }
+                    }
+                    sgn ^= syn[i];
+                    c2b[e] = ms_scaling_factor * pow(-1, sgn) * propagated; /* :631 */
+                    b2c[e] = llr[j];
+                    llr[j] += c2b[e];
+                }
+                dec[j] = (llr[j] <= 0) ? 1 : 0;
+                double t = 0;
+                for (int p = g.col_ptr[j + 1] - 1; p >= g.col_ptr[j]; p--) {
+                    int e = g.csc2csr[p];
+                    b2c[e] += t;
+                    t += c2b[e];
+                }
+            }
+            converged = 1; /* :646-660 */
+            for (int i = 0; i < m; i++) {
+                uint8_t x = 0;
+                for (int f = g.row_ptr[i]; f < g.row_ptr[i + 1]; f++) x ^= dec[g.col_idx[f]];
+                if (x != syn[i]) {
+                    converged = 0;
+                    break;
+                }
+            }
+            iterations = it;
+        }
+        memcpy(out_decoding + b * (int64_t) n, dec, (size_t) n);
+        if (out_converged) out_converged[b] = (uint8_t) converged;
+        if (out_iters) out_iters[b] = iterations;
+        if (out_llr) memcpy(out_llr + b * (int64_t) n, llr, sizeof(double) * (size_t) n);
+        if (out_soft) memcpy(out_soft + b * (int64_t) m, soft, sizeof(double) * (size_t) m);
+    }
+    free(b2c);
+    free(c2b);
+    free(llr);
+    free(soft);
+    free(syn);
+    free(dec);
+    bpo_graph_free(&g);
+    return 0;
+}
+
 /* gf2sparse.hpp:177-196: out = H v (mod 2), used for received-vector input (bp.hpp:164). */
 int bpo_mulvec(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *cols, const uint8_t *vecs,
                int64_t batch, uint8_t *out) {

@@ -136,6 +136,32 @@ double ref_decode_received(int m, int n, int64_t nnz, const int32_t *rows, const
     return 0.0;
 }
 
+// ldpc::bp::BpDecoder::soft_info_decode_serial (bp.hpp:547-665), one call per soft syndrome, one decoder object.
+double ref_soft_info_decode_batch(int m, int n, int64_t nnz, const int32_t *rows, const int32_t *cols,
+                                  const double *channel, int max_iter, double ms_scaling_factor,
+                                  const int32_t *serial_order, int serial_order_len, double cutoff, double sigma,
+                                  const double *soft_syndromes, int64_t batch, uint8_t *out_decoding,
+                                  uint8_t *out_converged, int32_t *out_iters, double *out_llr, double *out_soft) {
+    Worker w;
+    try {
+        build_worker(w, m, n, nnz, rows, cols, channel, max_iter, 1 /* minimum_sum */, 0 /* serial */,
+                     ms_scaling_factor, serial_order, serial_order_len, 0, 0);
+    } catch (...) {
+        return -1.0;
+    }
+    std::vector<double> soft((size_t) m);
+    for (int64_t b = 0; b < batch; b++) {
+        std::memcpy(soft.data(), soft_syndromes + b * (int64_t) m, sizeof(double) * (size_t) m);
+        w.bpd->soft_info_decode_serial(soft, cutoff, sigma);
+        std::memcpy(out_decoding + b * (int64_t) n, w.bpd->decoding.data(), (size_t) n);
+        if (out_converged) out_converged[b] = w.bpd->converge ? 1 : 0;
+        if (out_iters) out_iters[b] = w.bpd->iterations;
+        if (out_llr) std::memcpy(out_llr + b * (int64_t) n, w.bpd->log_prob_ratios.data(), sizeof(double) * (size_t) n);
+        if (out_soft) std::memcpy(out_soft + b * (int64_t) m, w.bpd->soft_syndrome.data(), sizeof(double) * (size_t) m);
+    }
+    return 0.0;
+}
+
 int ref_hardware_threads() { return (int) std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -159,3 +159,26 @@ def test_levelised_serial_schedule_is_equivalent(port_oracle, ref_oracle, method
             b = orc.decode_batch(H, syn, 0.05, serial_schedule_order=np.asarray(lev_order), **kw)
             assert_same_decode(a, b, llr_exact=True)
         assert not a[1].all() and a[1].any()
+
+
+def _soft_inputs(H, p, B, sigma, seed):
+    rng = np.random.default_rng(seed)
+    err = (rng.random((B, H.shape[1])) < p).astype(np.uint8)
+    syn = codes.syndromes_of(H, err)
+    return (1 - 2.0 * syn) + rng.normal(0, sigma, size=syn.shape)
+
+
+@pytest.mark.parametrize("mk,p", [(lambda: codes.rep_code(7), 0.1), (lambda: codes.regular_ldpc(240, 3, 6, seed=3), 0.05),
+                                  (lambda: codes.rotated_surface_code_x(7), 0.05), (codes.bivariate_bicycle_144, 0.02)],
+                         ids=["rep7", "ldpc240", "surface7", "bb144"])
+def test_port_soft_info_bit_identical_to_reference(port_oracle, ref_oracle, mk, p):
+    """soft_info_decode_serial (bp.hpp:547-665): restatement vs the reference, incl. the posterior LLRs and the soft
+    syndrome the virtual check updates leave behind, for cutoffs that never / sometimes / mostly trigger them."""
+    H = mk()
+    for sigma, cutoff, ms in ((0.6, np.inf, 1.0), (0.8, 3.0, 0.625), (1.2, 10.0, 0.9), (0.3, 1.0, 1.0)):
+        soft = _soft_inputs(H, p, 120, sigma, seed=int(sigma * 10))
+        a = port_oracle.soft_info_decode_batch(H, soft, p, 20, ms, cutoff, sigma)
+        b = ref_oracle.soft_info_decode_batch(H, soft, p, 20, ms, cutoff, sigma)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(a[3].view(np.uint64), b[3].view(np.uint64))
+        assert np.array_equal(a[4].view(np.uint64), b[4].view(np.uint64))
