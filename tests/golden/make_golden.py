@@ -36,8 +36,32 @@ CONFIGS = [
 ]
 
 
+# soft-information decoding (bp.hpp:547-665): name, H, p, shots, sigma, cutoff, ms_scaling_factor, max_iter
+SOFT_CONFIGS = [
+    ("f4_softinfo_ldpc240", codes.regular_ldpc(240, 3, 6, seed=3), 0.05, 48, 0.8, 3.0, 0.625, 20),
+    ("f4_softinfo_surface7", codes.rotated_surface_code_x(7), 0.05, 64, 0.5, 2.0, 1.0, 15),
+]
+
+
+def main_soft(ref, only):
+    for name, H, p, B, sigma, cutoff, ms, max_iter in SOFT_CONFIGS:
+        if only and name not in only:
+            continue
+        rng = np.random.default_rng(21)
+        err = (rng.random((B, H.shape[1])) < p).astype(np.uint8)
+        soft = (1 - 2.0 * codes.syndromes_of(H, err)) + rng.normal(0, sigma, size=(B, H.shape[0]))
+        dec, conv, its, llr, soft_out = ref.soft_info_decode_batch(H, soft, p, max_iter, ms, cutoff, sigma)
+        coo = sp.coo_matrix(H)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), rows=coo.row.astype(np.int32),
+                            cols=coo.col.astype(np.int32), shape=np.asarray(H.shape), channel=np.full(H.shape[1], p),
+                            soft=soft, decoding=dec, converged=conv, iters=its, llr=llr, soft_out=soft_out,
+                            max_iter=max_iter, ms_scaling_factor=ms, cutoff=cutoff, sigma=sigma, kind="soft_info")
+        print(name, soft.shape, "converged", conv.mean(), "mean iters", its.mean())
+
+
 def main():
     ref = oracle.RefOracle()
+    main_soft(ref, set(sys.argv[1:]))
     only = set(sys.argv[1:])  # optional: names of the fixtures to (re)generate
     for name, H, p, B, Bhard, kw in CONFIGS:
         if only and name not in only:

@@ -179,6 +179,18 @@ def test_golden_fixtures_from_reference(kernel):
     for path in paths:
         z = np.load(path, allow_pickle=False)
         H = sp.csr_matrix((np.ones(z["rows"].size, np.uint8), (z["rows"], z["cols"])), shape=tuple(z["shape"]))
+        if "kind" in z.files and str(z["kind"]) == "soft_info":
+            if kernel != FAMILIES[0]:
+                continue  # the soft-information kernel has no family choice: check it once
+            from ldpc_b200 import SoftInfoBpDecoder
+            d = SoftInfoBpDecoder(H, error_channel=z["channel"], max_iter=int(z["max_iter"]),
+                                  ms_scaling_factor=float(z["ms_scaling_factor"]), cutoff=float(z["cutoff"]),
+                                  sigma=float(z["sigma"]))
+            got = d.decode_batch(z["soft"], return_llr=True)
+            assert_same_decode((got, d.converge_batch, d.iter_batch, d.log_prob_ratios_batch),
+                               (z["decoding"], z["converged"], z["iters"], z["llr"]), llr_exact=True)
+            assert np.array_equal(d.soft_syndrome_batch.view(np.uint64), z["soft_out"].view(np.uint64))
+            continue
         if kernel in ("edge", "pair") and str(z["schedule"]) == "serial":
             continue
         dc, dv = int(np.diff(H.indptr).max()), int(np.diff(H.tocsc().indptr).max())

@@ -121,6 +121,12 @@ def test_port_matches_golden_fixture(port_oracle, path):
     z = np.load(path, allow_pickle=False)
     import scipy.sparse as sp
     H = sp.csr_matrix((np.ones(z["rows"].size, np.uint8), (z["rows"], z["cols"])), shape=tuple(z["shape"]))
+    if "kind" in z.files and str(z["kind"]) == "soft_info":  # soft_info_decode_serial fixtures (bp.hpp:547-665)
+        got = port_oracle.soft_info_decode_batch(H, z["soft"], z["channel"], int(z["max_iter"]),
+                                                 float(z["ms_scaling_factor"]), float(z["cutoff"]), float(z["sigma"]))
+        assert_same_decode(got[:4], (z["decoding"], z["converged"], z["iters"], z["llr"]), llr_exact=True)
+        assert np.array_equal(got[4].view(np.uint64), z["soft_out"].view(np.uint64))
+        return
     kw = dict(max_iter=int(z["max_iter"]), bp_method=str(z["bp_method"]), schedule=str(z["schedule"]),
               ms_scaling_factor=float(z["ms_scaling_factor"]))
     got = port_oracle.decode_batch(H, z["syndromes"], z["channel"], **kw)
