@@ -298,6 +298,7 @@ PairKernel pick_pair_bucket(int dc, int dv, bool regular, bool llr, int maxt) {
         return nullptr;
     }
     if (maxt != 512) return nullptr;
+    if (dc <= 4 && dv <= 2) { BPB_PICK(4, 2, 512, false); }  // surface codes: half the register arrays of (8, 4)
     if (dc <= 8 && dv <= 4) { BPB_PICK(8, 4, 512, false); }
     if (dc <= 8 && dv <= 16) { BPB_PICK(8, 16, 512, false); }
     if (dc <= 32 && dv <= 4) { BPB_PICK(32, 4, 512, false); }
