@@ -106,9 +106,10 @@ int bpb_osd0_host(bpb_decoder *h, const uint8_t *syndromes, const double *log_pr
                   const uint8_t *converged, int64_t batch, uint8_t *decoding, int threads);
 
 /* --- BP + OSD-0 for a whole batch: replaces BpOsdDecoder.decode (_bposd_decoder.pyx:78-136: bpd.decode, then
- * osdD.decode only when !bpd.converge) for `batch` syndromes.  BP runs on the device; the posterior LLRs stay on the
- * device except for the rows BP did not solve, which are gathered, copied back and solved by bpb_osd0_host's
- * elimination.  decoding [batch][n] receives the BP output for converged rows and the OSD-0 solution otherwise;
+ * osdD.decode only when !bpd.converge) for `batch` syndromes.  BP runs on the device and its posterior LLRs stay
+ * there.  OSD-0 for the rows BP did not solve runs on the device too (osd_device.cu) when the code fits that kernel
+ * and bpb_set_osd_location allows it (BPB_OSD_AUTO); otherwise those LLR rows are gathered, copied back and solved by
+ * bpb_osd0_host's elimination on `threads` host threads.  decoding [batch][n] receives the BP output for converged rows and the OSD-0 solution otherwise;
  * bp_decoding (optional, [batch][n]) receives the raw BP output; converged / iterations are BP's (may be NULL). */
 int bpb_bposd_decode_batch(bpb_decoder *h, const uint8_t *syndromes, int64_t batch, uint8_t *decoding,
                            uint8_t *converged, int32_t *iterations, uint8_t *bp_decoding, int threads);
